@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — ragnar's radiation hot path on B200, the metric BASELINE.json names:
+particle x photon-bin synchrotron evaluations per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2], "SynchrotronSpectrum_3D: 1e8 synthetic
+electrons in a random-angle uniform B field, 200 photon bins, 1 GPU"): per GPU,
+1e8 electrons with U1 ~ u^-2 on [1,100], E = 0, B an isotropic unit vector;
+photon bins Logbins(0.01, 1e5, 200, mec2); B0 = g_syn = e_syn_at_g_syn = 1.
+One *step* = one pass of the hot path over that batch:
+Particles.energyDistribution(Logbins(1e-2, 1e3, 200)) + SynchrotronSpectrum_3D.
+Evaluations per step = particles x photon bins (every pair the reference functor
+runs for).  N > 1: one process per GPU (torchrun), each rank owns
+1e8 particles of one global Philox stream (weak scaling); the per-rank spectrum
+and histogram partials are summed by one NCCL all-reduce each inside the call.
+
+`value` is timed with inputs resident in HBM; `e2e` is the same step through the
+C-ABI with HOST (pinned) particle columns, H2D of all nine columns and D2H of
+the results inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "synchrotron_particle_x_photon_bin_evals_per_sec"
+UNIT = "evals/s"
+N_PER_GPU = 100_000_000
+NBINS = 200
+PHOTON_BINS = (0.01, 1e5)
+GAMMA_BINS = (1e-2, 1e3, 200)
+CONSTS = (1.0, 1.0, 1.0)  # B0, g_syn, e_syn_at_g_syn
+SEED = 123
+CPU_SAMPLE = 1_000_000  # particles per CPU-baseline step (x 200 bins = 2e8 evals)
+
+
+def workload_config(n_per_gpu: int, nbins: int, ngpus: int) -> dict:
+    return {
+        "workload": "SynchrotronSpectrum_3D + Particles.energyDistribution, BASELINE configs[2]",
+        "particles_per_gpu": n_per_gpu,
+        "photon_bins": nbins,
+        "photon_bin_range_mec2": list(PHOTON_BINS),
+        "gamma_beta_bins": list(GAMMA_BINS),
+        "population": "U1~u^-2 on [1,100], E=0, B isotropic unit (device Philox4x32-10, seed 123)",
+        "sharding": f"particles/{ngpus} ranks, NCCL all-reduce of spectra" if ngpus > 1 else "none",
+        "cache": "inputs_larger_than_L2 (3.6 GB of particle columns per pass vs 126 MB L2)",
+    }
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.rows = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                     "-i", str(self.device)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# -------------------------------------------------------------- reference arm
+def _ref_module():
+    import oracle
+
+    if oracle.ref_available():
+        return oracle.ref(), "reference"
+    return None, "port"
+
+
+def cpu_step(sample_cols, bins, gbins):
+    """One bounded CPU sample of the step through the reference's own code path
+    (oracle/_ref = the reference sources on the Kokkos-subset OpenMP shim) or,
+    where that was never built, the C++ port.  Returns seconds."""
+    import contextlib
+    import io
+
+    import oracle
+
+    U, E, B = sample_cols
+    mod, kind = _ref_module()
+    t0 = time.perf_counter()
+    if mod is not None:
+        with contextlib.redirect_stdout(io.StringIO()):
+            p = mod.Particles_3D("e-")
+            p.fromArrays({f"{q}{d + 1}": a[d] for q, a in (("U", U), ("E", E), ("B", B))
+                          for d in range(3)})
+            t0 = time.perf_counter()  # the reference's fromArrays is not part of the metric
+            p.energyDistribution(mod.Logbins(*GAMMA_BINS))
+            mod.SynchrotronSpectrum_3D(p, mod.Logbins(*PHOTON_BINS, len(bins), "mec2"), *CONSTS)
+    else:
+        oracle.port.energy_distribution(*U, gbins, True, True)
+        oracle.port.sync_spectrum_particles(U, E, B, bins, *CONSTS)
+    return time.perf_counter() - t0, kind
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tests import synth
+
+    import oracle
+
+    nbins = args.bins
+    sample = min(args.cpu_sample, args.particles)
+    cols = synth.config3(sample, seed=SEED)
+    bins = oracle.port.logspace(*PHOTON_BINS, nbins)
+    gbins = oracle.port.logspace(*GAMMA_BINS)
+    cores = oracle.port.num_threads()
+    kind = "port"
+    for _ in range(args.warmup):
+        _, kind = cpu_step(cols, bins, gbins)
+    times = []
+    for _ in range(args.steps):
+        dt, kind = cpu_step(cols, bins, gbins)
+        times.append(dt)
+    total = sum(times)
+    value = sample * nbins * args.steps / total
+    sample_desc = (f"{sample} particles x {nbins} bins per step (first {sample} of the workload's "
+                   f"population, host-generated), {cores} OpenMP threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 terms (reference arithmetic)", "data": "synthetic",
+        "config": workload_config(args.particles, nbins, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------- our arm
+def run_ours(args) -> None:
+    import torch
+
+    from ragnar_b200 import cabi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cabi.init(local_rank)
+    from ragnar_b200 import dist as rdist
+
+    rdist.install_communicator(cabi, dist)
+    stream = torch.cuda.ExternalStream(cabi.stream_handle(), device=local_rank)
+
+    n, nbins = args.particles, args.bins
+    bins = cabi.logspace(*PHOTON_BINS, nbins)
+    gbins = cabi.logspace(*GAMMA_BINS)
+    table = cabi.tabulate_ffunc()
+    prtls = cabi.Particles(3).allocate(n)
+    # rank r owns global particle indices [r*n, (r+1)*n) of one Philox stream
+    prtls.generate(0, SEED, rank * n, 0, n, 1.0, 100.0)
+    cabi.synchronize()
+
+    def barrier():
+        cabi.synchronize()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kernel_ms = {"hist": [], "spec": []}
+
+    def step():
+        hist = cabi.energy_histogram(prtls, gbins, True, True, want_counts=False)
+        kernel_ms["hist"].append(cabi.last_kernel_ms()[1])
+        spec = cabi.sync_spectrum_particles(prtls, bins, *CONSTS, table=table)
+        kernel_ms["spec"].append(cabi.last_kernel_ms()[1])
+        return hist, spec
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    kernel_ms = {"hist": [], "spec": []}
+    launches0 = cabi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            hist, spec = step()
+        ev1.record(stream)
+        barrier()
+    launches = cabi.launch_count() - launches0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n * nbins / (ms_per_step * 1e-3)
+
+    # ---- end-to-end: host (pinned) columns in, results out, every step
+    e2e = None
+    if not args.no_e2e:
+        pinned = [cabi.PinnedArray(n) for _ in range(9)]
+        k = 0
+        for q in (cabi.Q_U, cabi.Q_E, cabi.Q_B):
+            for d in range(3):
+                cabi.check(cabi.lib().rgc_particles_read(prtls.h, q, d, 0, n,
+                                                         pinned[k].array.ctypes.data))
+                k += 1
+        target = cabi.Particles(3).allocate(n)
+        target.n = n
+
+        def e2e_step():
+            k = 0
+            for q in (cabi.Q_U, cabi.Q_E, cabi.Q_B):
+                for d in range(3):
+                    target.write(q, d, 0, pinned[k].array)
+                    k += 1
+            h = cabi.energy_histogram(target, gbins, True, True, want_counts=False)
+            s = cabi.sync_spectrum_particles(target, bins, *CONSTS, table=table)
+            return h, s
+
+        e2e_step()
+        barrier()
+        e2e_steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            h_e2e, s_e2e = e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * nbins * e2e_steps / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": 9 * 4 * n + 4 * (nbins + len(gbins)),
+               "d2h_bytes_per_step": 12 * (nbins + len(gbins)),
+               "steps": e2e_steps, "ms_per_step": 1e3 * float(dt.item()) / e2e_steps,
+               "timer": "host wall clock around the C-ABI calls, max over ranks"}
+        assert np.array_equal(s_e2e[1], spec[1]), "e2e result differs from the resident run"
+        for p in pinned:
+            p.close()
+        target.release()
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (sync_spectrum_kernel), measured live
+    peaks = {}
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peaks = json.loads(peaks_path.read_text())
+    clk = clocks.summary()
+    spec_ms = statistics.mean(kernel_ms["spec"])
+    hist_ms = statistics.mean(kernel_ms["hist"])
+    sm_count = cabi.device_info()[1]
+    evals_per_launch = n * nbins
+    # shared-memory gather roofline: 8 B per evaluation vs 128 B/clk/SM
+    sm_mhz = clk["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
+    lds_peak = 128.0 * sm_count * sm_mhz * 1e6 / 1e9  # GB/s at the clock seen under load
+    lds_achieved = evals_per_launch * 8 / (spec_ms * 1e-3) / 1e9
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {
+        "kernel": "sync_spectrum_kernel", "bound": "lds",
+        "achieved": lds_achieved, "peak": lds_peak, "unit": "GB/s",
+        "frac": lds_achieved / lds_peak, "traffic": None,
+        "peak_source": "128 B/clk/SM x SMs x median SM clock sampled during the timed region "
+                       "(shared-memory gather, not HBM: 36 B of HBM per particle are amortised "
+                       "over the photon bins)",
+        "evals_per_s": evals_per_launch / (spec_ms * 1e-3), "ms_per_launch": spec_ms,
+        "hbm_gbs_of_this_kernel": n * 36 / (spec_ms * 1e-3) / 1e9,
+    }
+    roofline_hist = {
+        "kernel": "energy_hist_kernel", "bound": "hbm",
+        "achieved": n * 12 / (hist_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": n * 12 / (hist_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+        "particles_per_s": n / (hist_ms * 1e-3), "ms_per_launch": hist_ms,
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        sample = min(args.cpu_sample, n)
+        cols = [[prtls.read(q, d, 0, sample) for d in range(3)]
+                for q in (cabi.Q_U, cabi.Q_E, cabi.Q_B)]
+        obins = oracle.port.logspace(*PHOTON_BINS, nbins)
+        ogbins = oracle.port.logspace(*GAMMA_BINS)
+        dt, kind = cpu_step(cols, obins, ogbins)
+        cpu_baseline = {
+            "value": sample * nbins / dt, "unit": UNIT, "cores": oracle.port.num_threads(),
+            "kind": kind,
+            "sample": f"first {sample} particles of the workload x {nbins} bins, one pass "
+                      f"({dt:.1f} s)",
+        }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 terms, fp64 accumulation",
+        "data": "synthetic", "config": workload_config(n, nbins, world),
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_histogram_kernel": roofline_hist,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--particles", type=int, default=N_PER_GPU, help="particles per GPU")
+    ap.add_argument("--bins", type=int, default=NBINS)
+    ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,241 @@
+/*
+ * ragnar_cuda.h — C-ABI of libragnar_cuda.so, the B200 (sm_100a) implementation
+ * of ragnar's radiation hot path.
+ *
+ * This is the drop-in boundary: every entry point is what the reference's own
+ * C++ layer (haykh/ragnar @ fceb6b08) would bind in place of the Kokkos code it
+ * replaces; the reference interface each one stands in for is cited as
+ * path:line relative to the reference root.  Plain C: opaque handles, raw
+ * pointers and sizes; no CUDA, torch or C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a non-zero RGC_ERR_* code otherwise;
+ *     rgc_last_error() then holds a thread-local message (CUDA / NCCL / HDF5
+ *     error text included).  The reference throws C++ exceptions at the same
+ *     points; the host layer (ragnar_b200/csrc/host) re-throws them.
+ *   - "host" pointers may be pageable or pinned (rgc_host_alloc); pinned ones are
+ *     copied with one async DMA, pageable ones are staged through a pinned ring.
+ *   - calls are synchronous at return (the reference calls Kokkos::fence()
+ *     before returning to Python: src/physics/synchrotron.cpp:102,142,
+ *     src/containers/particles.cpp:256) unless documented otherwise.
+ *   - there is NO CPU fallback: without a CUDA device rgc_init() fails and every
+ *     compute entry point returns RGC_ERR_NOT_INITIALIZED.
+ */
+#ifndef RAGNAR_CUDA_H
+#define RAGNAR_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* every entry point below is exported; the rest of the library is hidden */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define RGC_OK                  0
+#define RGC_ERR_INVALID         1 /* bad argument (-> std::runtime_error / range_error upstream) */
+#define RGC_ERR_NOT_INITIALIZED 2 /* rgc_init() not called or no CUDA device */
+#define RGC_ERR_CUDA            3 /* a CUDA runtime call failed */
+#define RGC_ERR_NCCL            4 /* an NCCL call failed / libnccl not loadable */
+#define RGC_ERR_IO              5 /* file / HDF5 format error */
+#define RGC_ERR_OOM             6 /* device or pinned-host allocation failed */
+
+/* element types of rgc_buf_t — Array1D<int|float|double>, src/containers/array.hpp:15-42 */
+#define RGC_I32 0
+#define RGC_F32 1
+#define RGC_F64 2
+
+/* particle quantities — Particles<D>::X,U,E,B, src/containers/particles.hpp:19-20 */
+#define RGC_Q_X 0
+#define RGC_Q_U 1
+#define RGC_Q_E 2
+#define RGC_Q_B 3
+
+typedef struct rgc_buf       rgc_buf_t;       /* 1-D device array            */
+typedef struct rgc_particles rgc_particles_t; /* SoA particle container      */
+
+/* ------------------------------------------------------------------ runtime */
+
+/* Kokkos::initialize() — src/pyinterface.cpp:30-39.  device < 0 selects
+ * $LOCAL_RANK (one process per GPU under torchrun) or 0.  Idempotent. */
+int rgc_init(int device);
+/* Kokkos::finalize() — src/pyinterface.cpp:40-49 */
+int rgc_finalize(void);
+int rgc_is_initialized(void);
+int rgc_device_count(int* count);
+/* device ordinal, SM count and total HBM bytes of the active device */
+int rgc_device_info(int* device, int* sm_count, size_t* hbm_bytes);
+/* the library's compute stream (cudaStream_t) for event timing by harnesses */
+int         rgc_stream(void** stream);
+int         rgc_synchronize(void);
+const char* rgc_last_error(void);
+/* number of kernels this library has launched since rgc_init (bench evidence) */
+uint64_t rgc_launch_count(void);
+
+/* pinned host memory for zero-staging H2D/D2H (cudaHostAlloc / cudaFreeHost) */
+int rgc_host_alloc(size_t bytes, void** ptr);
+int rgc_host_free(void* ptr);
+
+/* ------------------------------------------------- multi-GPU (one rank/GPU) */
+
+/* One process per GPU.  Rank 0 obtains an id, the launcher broadcasts its
+ * RGC_COMM_ID_BYTES to all ranks out of band (torch.distributed / MPI / file),
+ * every rank calls rgc_comm_init.  While a communicator is installed,
+ * rgc_energy_histogram and rgc_sync_spectrum_particles all-reduce (sum) their
+ * fp64 / u64 partials with ONE ncclAllReduce each, enqueued on the compute
+ * stream right behind the reduction kernel.  The reference has no multi-GPU
+ * path at all. */
+#define RGC_COMM_ID_BYTES 128
+int rgc_comm_get_unique_id(unsigned char id[RGC_COMM_ID_BYTES]);
+int rgc_comm_init(const unsigned char id[RGC_COMM_ID_BYTES], int rank, int nranks);
+int rgc_comm_destroy(void);
+int rgc_comm_info(int* rank, int* nranks); /* 0,1 when no communicator */
+
+/* -------------------------------------------- Array1D<T> device buffers */
+
+/* Kokkos::View<T*>{label, n} (zero-initialised) */
+int rgc_buf_create(int dtype, size_t n, rgc_buf_t** out);
+/* Array1D(const py::array_t<T>&) — src/containers/array.hpp:20-30 */
+int rgc_buf_from_host(int dtype, const void* host, size_t n, rgc_buf_t** out);
+/* Array1D::as_array / as_vector / head — src/containers/array.cpp:18-60 */
+int    rgc_buf_to_host(const rgc_buf_t* buf, size_t start, size_t n, void* host);
+size_t rgc_buf_size(const rgc_buf_t* buf);
+int    rgc_buf_dtype(const rgc_buf_t* buf);
+/* raw device pointer (for harnesses that time kernels / share memory with torch) */
+void* rgc_buf_device_ptr(const rgc_buf_t* buf);
+/* Kokkos::View handles are ref-counted; so are these */
+int rgc_buf_retain(rgc_buf_t* buf);
+int rgc_buf_release(rgc_buf_t* buf);
+
+/* ------------------------------------------------------------- Particles<D> */
+
+/* Particles<D>(label) — src/containers/particles.hpp:22 (label stays host-side) */
+int rgc_particles_create(int dim, rgc_particles_t** out);
+int rgc_particles_release(rgc_particles_t* p);
+/* Particles<D>::allocate — src/containers/particles.cpp:115-130: zero-filled SoA
+ * columns U1..3,E1..3,B1..3 (+X1..XD when with_coords) of nalloc floats each */
+int rgc_particles_allocate(rgc_particles_t* p, size_t nalloc, int with_coords);
+/* Particles<D>::reallocate — src/containers/particles.cpp:132-187: grow, keep data */
+int rgc_particles_reallocate(rgc_particles_t* p, size_t nalloc);
+/* add (zeroed) coordinate columns to a container allocated without them */
+int    rgc_particles_enable_coords(rgc_particles_t* p);
+int    rgc_particles_has_coords(const rgc_particles_t* p);
+size_t rgc_particles_nalloc(const rgc_particles_t* p);
+int    rgc_particles_dim(const rgc_particles_t* p);
+/* one column of fromArrays / readPrtlQuantity: host[0..n) -> column (quantity,
+ * comp) at [start, start+n).  src/containers/particles.cpp:56-98,
+ * src/plugins/tristan-v2.cpp:76-93.  Asynchronous: returns once the source
+ * buffer may be reused; rgc_synchronize() (or any compute call) orders it. */
+int rgc_particles_write(rgc_particles_t* p, int quantity, int comp, size_t start,
+                        const float* host, size_t n);
+/* getSubview — src/containers/particles.cpp:346-383: column -> host / new buffer */
+int rgc_particles_read(const rgc_particles_t* p, int quantity, int comp, size_t start,
+                       size_t n, float* host);
+int rgc_particles_column(const rgc_particles_t* p, int quantity, int comp, size_t n,
+                         rgc_buf_t** out);
+/* raw device pointer of a column (harness use) */
+void* rgc_particles_device_ptr(const rgc_particles_t* p, int quantity, int comp);
+
+/* Synthetic populations generated ON DEVICE (counter-based Philox4x32-10 keyed by
+ * (seed, global particle index), so any shard of any size reproduces the same
+ * particles).  Used by bench.py / tests for N too large to stage through the
+ * host.  Fills U,E,B of [start, start+n) for global indices
+ * [global_offset, global_offset+n).
+ *   kind 0  "config 3": |U| power law p=-2 on [1,100] along x, E=0, B isotropic unit
+ *   kind 1  "full 3-D": isotropic U, |U| power law p=-2 on [umin,umax],
+ *                        |B| in [0.5,2] isotropic, E = 0.1 * (B x random unit)
+ *   kind 2  "config 2": isotropic U, |U| power law p=-2 on [umin,umax], E=B=0 */
+int rgc_particles_generate(rgc_particles_t* p, int kind, uint64_t seed,
+                           uint64_t global_offset, size_t start, size_t n, float umin,
+                           float umax);
+
+/* -------------------------------------------------- host-exact small pieces */
+
+/* Linspace / Logspace — src/utils/snippets.cpp:21-62 (bit-identical bin edges
+ * are a precondition of bit-exact histograms; evaluated on the host with the
+ * reference's exact float/double promotions) */
+int rgc_linspace(float start, float stop, size_t num, float* out);
+int rgc_logspace(float start, float stop, size_t num, float* out);
+/* sync::Ffunc_integrand — src/physics/synchrotron.cpp:28-46 */
+int rgc_sync_ffunc_integrand(float x, float* out);
+/* sync::TabulateFfunc — src/physics/synchrotron.cpp:48-65 (cached per (n,xmin,xmax)) */
+int rgc_sync_tabulate_ffunc(size_t npoints, float xmin, float xmax, float* xs, float* ys);
+/* InterpolateTabulatedFunction<LG> — src/containers/tabulation.hpp:19-53 (host scalar) */
+int rgc_interpolate(int loggrid, float x0, const float* x, const float* y, size_t n,
+                    float yfill, float* out);
+/* generators — src/containers/distributions.cpp:37-130.  kind 0 Plaw(p,emin,emax),
+ * 1 BrokenPlaw(e_break,p1,p2,emin,emax), 2 Delta(energy0,denergy); params in that order */
+int rgc_generator_eval(int kind, const float* params, const float* energy, size_t n,
+                       float* out);
+
+/* ------------------------------------------------------------- the hot path */
+
+/* Particles<D>::energyDistribution — src/containers/particles.cpp:189-260.
+ * bins: n host floats (left edges; index formula is logarithmic whatever
+ * log_spaced says, exactly as the reference).  Over particles [0, nactive):
+ *   out_hist[n]    float  sum of 1/energy (log_spaced) or particle count (!log_spaced),
+ *                         accumulated wide and rounded once
+ *   out_counts[n]  u64    particle counts per bin (bit-exact vs the reference's index)
+ *   out_sum64[n]   double the wide sum before rounding           (each may be NULL)
+ * With a communicator installed the sums are all-reduced over ranks. */
+int rgc_energy_histogram(const rgc_particles_t* p, size_t nactive, const float* bins,
+                         size_t n, int log_spaced, int fourvel, float* out_hist,
+                         uint64_t* out_counts, double* out_sum64);
+
+/* SynchrotronSpectrum<D> + sync::Kernel<D> — src/physics/synchrotron.cpp:107-145,
+ * src/physics/synchrotron.hpp:103-233.  bins_e_syn: nbins host floats (units are
+ * checked by the caller, synchrotron.hpp:139-142); (tab_x, tab_y): the F(x) table
+ * of sync::TabulateFfunc (log grid).  out_spec[nbins] float, out_spec64 (optional)
+ * the fp64 sums it was rounded from.  All-reduced over ranks when a communicator
+ * is installed. */
+int rgc_sync_spectrum_particles(const rgc_particles_t* p, size_t nactive,
+                                const float* bins_e_syn, size_t nbins, const float* tab_x,
+                                const float* tab_y, size_t tab_n, float B0, float g_syn,
+                                float e_syn_at_g_syn, float* out_spec, double* out_spec64);
+
+/* SynchrotronSpectrumFromDist + sync::KernelFromDist —
+ * src/physics/synchrotron.cpp:69-105, src/physics/synchrotron.hpp:41-96.
+ * (gbeta, f): the TabulatedDistribution (ndist host floats each).  Replicated,
+ * never all-reduced. */
+int rgc_sync_spectrum_dist(const float* gbeta, const float* f, size_t ndist,
+                           int islog_bins_prtls, const float* bins_e_syn, size_t nbins,
+                           const float* tab_x, const float* tab_y, size_t tab_n, float g_syn,
+                           float e_syn_at_g_syn, float* out_spec, double* out_spec64);
+
+/* Device time (ms, CUDA events on the compute stream) of the kernels of the last
+ * hot-path call on this thread: [0] total, [1] dominant kernel only. */
+int rgc_last_kernel_ms(float ms[2]);
+
+/* ------------------------------------------------------ Tristan-v2 plugin */
+
+/* TristanV2<D>::readParticles — src/plugins/tristan-v2.cpp:95-188.  Opens
+ * <path>/output/prtl/prtl.tot.<step:05d> (HDF5), reads x_/y_/z_ (first dim, unless
+ * ignore_coords), u_/v_/w_, ex_/ey_/ez_, bx_/by_/bz_<sp> as float32 hyperslabs
+ * [start, start+count*stride) and streams them disk -> pinned ring -> device.
+ * *ntotal receives the dataset length, *nread the particles stored.  Validation
+ * (stride == 0, stride != 1 with size != 0, start + size >= ntotal) follows
+ * tristan-v2.cpp:102-107,126-128 and returns RGC_ERR_INVALID with the reference's
+ * message. */
+int rgc_tristan_read_particles(const char* path, size_t step, unsigned sp, size_t start,
+                               size_t size, size_t stride, int ignore_coords, int dim,
+                               rgc_particles_t** out, size_t* ntotal, size_t* nread);
+/* writes a synthetic Tristan-v2 particle file (test / bench fixture generator):
+ * datasets named as above for species sp, n floats each, contiguous float32.
+ * columns[k] may be NULL (dataset of zeros).  append != 0 adds a species to an
+ * existing file written by this function. */
+int rgc_tristan_write_species(const char* path, size_t step, unsigned sp, size_t n,
+                              int with_coords, const float* const* columns, int append);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RAGNAR_CUDA_H */

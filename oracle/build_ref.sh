@@ -34,7 +34,9 @@ build_one() { # name extra-flags
     return
   fi
   echo "build_ref.sh: building $target"
-  g++ $FLAGS "-Dragnar=$name" "$@" $INCS $SRCS -o "$target"
+  # PYBIND11_BUILD_ABI gives each oracle module a private pybind11 type registry,
+  # so ragnar_ref, ragnar_ref64 and the product module import side by side.
+  g++ $FLAGS "-Dragnar=$name" "-DPYBIND11_BUILD_ABI=\"_oracle_$name\"" "$@" $INCS $SRCS -o "$target"
 }
 build_one ragnar_ref &
 build_one ragnar_ref64 -DRAGNAR_ORACLE_SCATTER64 &

@@ -1,0 +1,136 @@
+// Synchrotron spectrum entry points — host-side mirror of the reference's
+// src/physics/synchrotron.cpp drivers: same banners, same argument checks, the
+// compute itself is one C-ABI call into the sm_100a kernels.
+#include "docstrings.hpp"
+#include "ragnar_host.hpp"
+
+using namespace pybind11::literals;
+
+namespace rgb {
+
+  real_t Ffunc_integrand(real_t x) {
+    real_t out = 0.0f;
+    check(rgc_sync_ffunc_integrand(x, &out));
+    return out;
+  }
+
+  // reference synchrotron.cpp:48-65 — built on the host (libstdc++ cyl_bessel_k)
+  // once per (npoints, xmin, xmax) and cached inside libragnar_cuda
+  TabulatedFunction<true> TabulateFfunc(std::size_t npoints, real_t xmin, real_t xmax) {
+    std::vector<real_t> xs(npoints), ys(npoints);
+    check(rgc_sync_tabulate_ffunc(npoints, xmin, xmax, xs.data(), ys.data()));
+    return TabulatedFunction<true> { Array1D<real_t> { xs }, Array1D<real_t> { ys } };
+  }
+
+  namespace {
+    struct FTable {
+      std::vector<real_t> x, y;
+    };
+
+    const FTable& default_ftable() {
+      static FTable tab = [] {
+        FTable t;
+        t.x.resize(200);
+        t.y.resize(200);
+        check(rgc_sync_tabulate_ffunc(200, static_cast<real_t>(1e-6), static_cast<real_t>(100),
+                                      t.x.data(), t.y.data()));
+        return t;
+      }();
+      return tab;
+    }
+  } // namespace
+
+  // reference synchrotron.cpp:69-105
+  Array1D<real_t> SynchrotronSpectrumFromDist(const TabulatedDistribution& dist_prtls,
+                                              const Bins& bins_e_syn, real_t g_syn,
+                                              real_t e_syn_at_g_syn) {
+    py::print("Computing synchrotron spectrum from a distribution", "flush"_a = true);
+    const auto& tab   = default_ftable();
+    const auto  nbins = bins_e_syn.extent(0);
+    py::print(" Launching", human_readable((double)(dist_prtls.extent() * nbins)), "threads",
+              "end"_a = "", "flush"_a = true);
+    std::vector<real_t> spec(nbins, 0.0f);
+    check(rgc_sync_spectrum_dist(dist_prtls.EnergyBins().host_data(), dist_prtls.F().host_data(),
+                                 dist_prtls.extent(), dist_prtls.log_spaced() ? 1 : 0,
+                                 bins_e_syn.host_data(), nbins, tab.x.data(), tab.y.data(),
+                                 tab.x.size(), g_syn, e_syn_at_g_syn, spec.data(), nullptr));
+    py::print(": OK", "flush"_a = true);
+    return Array1D<real_t> { spec };
+  }
+
+  // reference synchrotron.cpp:107-145; the unit check of sync::Kernel's constructor
+  // (synchrotron.hpp:139-142) fires after the " Launching" line there too
+  template <dim_t D>
+  Array1D<real_t> SynchrotronSpectrum(const Particles<D>& prtls, const Bins& bins_e_syn,
+                                      real_t B0, real_t g_syn, real_t e_syn_at_g_syn) {
+    py::print("Computing synchrotron spectrum for", prtls.label(), "flush"_a = true);
+    const auto& tab   = default_ftable();
+    const auto  nbins = bins_e_syn.extent(0);
+    py::print(" Launching", human_readable((double)(prtls.nactive() * nbins)), "threads",
+              "end"_a = "", "flush"_a = true);
+    if (bins_e_syn.unit != EnergyUnits::mec2 and bins_e_syn.unit != EnergyUnits::mpc2) {
+      throw std::runtime_error("bins_e_syn must be in units of mc^2");
+    }
+    std::vector<real_t> spec(nbins, 0.0f);
+    if (prtls.is_allocated() && prtls.nactive() > 0) {
+      check(rgc_sync_spectrum_particles(prtls.handle(), prtls.nactive(), bins_e_syn.host_data(),
+                                        nbins, tab.x.data(), tab.y.data(), tab.x.size(), B0,
+                                        g_syn, e_syn_at_g_syn, spec.data(), nullptr));
+    }
+    py::print(": OK", "flush"_a = true);
+    return Array1D<real_t> { spec };
+  }
+
+  template Array1D<real_t> SynchrotronSpectrum(const Particles<1>&, const Bins&, real_t, real_t,
+                                               real_t);
+  template Array1D<real_t> SynchrotronSpectrum(const Particles<2>&, const Bins&, real_t, real_t,
+                                               real_t);
+  template Array1D<real_t> SynchrotronSpectrum(const Particles<3>&, const Bins&, real_t, real_t,
+                                               real_t);
+
+  void define_synchrotron(py::module& m) {
+    m.def("SynchrotronSpectrum_1D", &SynchrotronSpectrum<1>, "prtls"_a, "bins_e_syn"_a, "B0"_a,
+          "g_syn"_a, "e_syn_at_g_syn"_a, doc::SynchrotronSpectrum);
+    m.def("SynchrotronSpectrum_2D", &SynchrotronSpectrum<2>, "prtls"_a, "bins_e_syn"_a, "B0"_a,
+          "g_syn"_a, "e_syn_at_g_syn"_a, doc::SynchrotronSpectrum);
+    m.def("SynchrotronSpectrum_3D", &SynchrotronSpectrum<3>, "prtls"_a, "bins_e_syn"_a, "B0"_a,
+          "g_syn"_a, "e_syn_at_g_syn"_a, doc::SynchrotronSpectrum);
+    m.def("Ffunc_integrand", &Ffunc_integrand, "x"_a);
+    m.def("SynchrotronSpectrumFromDist", &SynchrotronSpectrumFromDist, "dist_prtls"_a,
+          "bins_e_syn"_a, "g_syn"_a, "e_syn_at_g_syn"_a, doc::SynchrotronSpectrumFromDist);
+  }
+
+  // exported with the reference's signatures and
+  // docstrings, not implemented yet (there is no CPU path to route them to)
+  void define_not_yet(py::module& m) {
+    m.def(
+      "ICSpectrum",
+      [](const TabulatedDistribution&, const TabulatedDistribution&, const Bins&) -> Array1D<real_t> {
+        PyErr_SetString(PyExc_NotImplementedError,
+                        "ICSpectrum is outside the B200 hot path of this build (SURVEY.md 8f-f1)");
+        throw py::error_already_set();
+      },
+      "dist_prtls"_a, "dist_soft_photons"_a, "bins_e_ic"_a, doc::ICSpectrum);
+    for (const char* suffix : { "i", "f", "d" }) {
+      m.def(
+        (std::string("H5read1DArray_") + suffix).c_str(),
+        [](const std::string&, const std::string&, std::size_t, std::size_t) {
+          PyErr_SetString(PyExc_NotImplementedError,
+                          "generic HDF5 array I/O is outside the B200 hot path of this build "
+                          "(SURVEY.md 8f-f2)");
+          throw py::error_already_set();
+        },
+        "filename"_a, "dsetname"_a, "size"_a = 0, "stride"_a = 1, doc::H5read1DArray);
+      m.def(
+        (std::string("H5write1DArray_") + suffix).c_str(),
+        [](const std::string&, const std::string&, const py::object&) {
+          PyErr_SetString(PyExc_NotImplementedError,
+                          "generic HDF5 array I/O is outside the B200 hot path of this build "
+                          "(SURVEY.md 8f-f2)");
+          throw py::error_already_set();
+        },
+        "filename"_a, "dsetname"_a, "array"_a, doc::H5write1DArray);
+    }
+  }
+
+} // namespace rgb

@@ -1,0 +1,132 @@
+// Internal declarations shared by the translation units of libragnar_cuda.so.
+// Not part of the C-ABI (include/ragnar_cuda.h is).
+#ifndef RGC_INTERNAL_HPP
+#define RGC_INTERNAL_HPP
+
+#include "ragnar_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace rgc {
+
+  // ------------------------------------------------------------------ errors
+  int  fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+  void clear_error();
+
+#define RGC_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t rgc_err__ = (expr);                                                 \
+    if (rgc_err__ != cudaSuccess) {                                                 \
+      return ::rgc::fail(rgc_err__ == cudaErrorMemoryAllocation ? RGC_ERR_OOM       \
+                                                                : RGC_ERR_CUDA,     \
+                         "%s failed: %s (%s:%d)", #expr,                            \
+                         cudaGetErrorString(rgc_err__), __FILE__, __LINE__);        \
+    }                                                                               \
+  } while (0)
+
+#define RGC_TRY(expr)               \
+  do {                              \
+    int rgc_rc__ = (expr);          \
+    if (rgc_rc__ != RGC_OK) {       \
+      return rgc_rc__;              \
+    }                               \
+  } while (0)
+
+#define RGC_REQUIRE_INIT()                                                          \
+  do {                                                                              \
+    if (!::rgc::ctx().initialized) {                                                \
+      return ::rgc::fail(RGC_ERR_NOT_INITIALIZED,                                   \
+                         "ragnar_cuda is not initialized (call rgc_init; a CUDA "   \
+                         "device is required, there is no CPU fallback)");          \
+    }                                                                               \
+  } while (0)
+
+  // ----------------------------------------------------------------- context
+  constexpr std::size_t kStageBytes = std::size_t(32) << 20; // per pinned stage
+  constexpr int         kNumStages  = 2;
+
+  struct Context {
+    bool         initialized { false };
+    int          device { 0 };
+    int          sm_count { 0 };
+    std::size_t  hbm_bytes { 0 };
+    cudaStream_t stream { nullptr };      // compute + ordered copies
+    cudaStream_t copy_stream { nullptr }; // bulk H2D of particle columns
+    // pinned staging ring for pageable host sources
+    void*       stage[kNumStages] { nullptr, nullptr };
+    cudaEvent_t stage_free[kNumStages] { nullptr, nullptr };
+    // event pair for rgc_last_kernel_ms
+    cudaEvent_t ev[4] { nullptr, nullptr, nullptr, nullptr };
+    float       last_ms[2] { 0.f, 0.f };
+    // NCCL (dlopen'ed lazily)
+    void* nccl_comm { nullptr };
+    int   rank { 0 };
+    int   nranks { 1 };
+    // reusable device scratch (grown on demand, freed in rgc_finalize)
+    void*       scratch { nullptr };
+    std::size_t scratch_bytes { 0 };
+    std::atomic<std::uint64_t> launches { 0 };
+  };
+
+  Context& ctx();
+  int      ensure_scratch(std::size_t bytes, void** out);
+  inline void count_launch(int n = 1) { ctx().launches.fetch_add((std::uint64_t)n); }
+
+  // all-reduce (sum) in place on the compute stream; no-op without a communicator
+  int allreduce_sum_f64(double* dev, std::size_t n);
+  int allreduce_sum_u64(unsigned long long* dev, std::size_t n);
+
+  // host -> device copy that accepts pageable or pinned sources (see rgc_runtime.cu)
+  int copy_h2d(void* dst, const void* src, std::size_t bytes, cudaStream_t stream);
+
+  // ------------------------------------------------------------ host math
+  // (rgc_hostmath.cpp, compiled by g++ with -ffp-contract=off: these reproduce
+  // the reference's float/double promotions on the host)
+  void  host_linspace(float start, float stop, std::size_t num, float* out);
+  void  host_logspace(float start, float stop, std::size_t num, float* out);
+  float host_ffunc_integrand(float x);
+  void  host_tabulate_ffunc(std::size_t n, float xmin, float xmax, float* xs, float* ys);
+  float host_interpolate(bool loggrid, float x0, const float* x, const float* y,
+                         std::size_t n, float yfill);
+  int   host_generator_eval(int kind, const float* params, const float* energy,
+                            std::size_t n, float* out);
+  // reference bin index of the energy histogram as a function of Usqr (float)
+  std::size_t host_energy_bin_index(float Usqr, bool fourvel, float energy_min,
+                                    float energy_max, std::size_t n);
+  double      host_energy_from_usqr(float Usqr, bool fourvel);
+
+} // namespace rgc
+
+// ------------------------------------------------------------ opaque handles
+struct rgc_buf {
+  std::atomic<int> refcount { 1 };
+  int              dtype { RGC_F32 };
+  std::size_t      n { 0 };
+  void*            dev { nullptr };
+};
+
+struct rgc_particles {
+  int         dim { 3 };
+  std::size_t nalloc { 0 };
+  std::size_t pitch { 0 }; // floats per column (nalloc rounded up to 64)
+  bool        allocated { false };
+  bool        with_coords { false };
+  float*      col[4][3] { { nullptr, nullptr, nullptr },
+                          { nullptr, nullptr, nullptr },
+                          { nullptr, nullptr, nullptr },
+                          { nullptr, nullptr, nullptr } };
+};
+
+namespace rgc {
+  inline std::size_t dtype_size(int dtype) { return dtype == RGC_F64 ? 8 : 4; }
+} // namespace rgc
+
+#endif // RGC_INTERNAL_HPP

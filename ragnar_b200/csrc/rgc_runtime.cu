@@ -1,0 +1,683 @@
+// Runtime of libragnar_cuda.so: context, errors, Array1D buffers, the SoA
+// Particles container, host<->device staging and the NCCL communicator.
+//
+// Replaces (reference paths relative to haykh/ragnar @ fceb6b08):
+//   Kokkos::initialize/finalize            src/pyinterface.cpp:30-49
+//   Kokkos::View<T*> + mirror/deep_copy    src/containers/array.{hpp,cpp}
+//   Particles<D> storage                   src/containers/particles.cpp:115-187,346-383
+// Data layout in HBM: every particle quantity component is its own contiguous
+// float column (SoA), 256-byte aligned, zero-initialised, so that a warp reads
+// 32 consecutive particles of one component with one 128-byte request and a
+// thread reads 4 consecutive particles with one 16-byte load.
+#include "rgc_internal.hpp"
+
+#include <dlfcn.h>
+#include <nccl.h> // types and enum values only; the library is dlopen'ed
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+namespace rgc {
+
+  // ------------------------------------------------------------------ errors
+  static thread_local std::string t_last_error;
+
+  int fail(int code, const char* fmt, ...) {
+    char    buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+    return code;
+  }
+
+  void clear_error() { t_last_error.clear(); }
+
+  Context& ctx() {
+    static Context c;
+    return c;
+  }
+
+  int ensure_scratch(std::size_t bytes, void** out) {
+    auto& c = ctx();
+    if (bytes > c.scratch_bytes) {
+      if (c.scratch) {
+        RGC_CUDA(cudaStreamSynchronize(c.stream));
+        RGC_CUDA(cudaFree(c.scratch));
+        c.scratch       = nullptr;
+        c.scratch_bytes = 0;
+      }
+      const std::size_t want = (bytes + (std::size_t(1) << 20) - 1) & ~((std::size_t(1) << 20) - 1);
+      RGC_CUDA(cudaMalloc(&c.scratch, want));
+      c.scratch_bytes = want;
+    }
+    *out = c.scratch;
+    return RGC_OK;
+  }
+
+  // ------------------------------------------------------------ H2D staging
+  static int ensure_stages() {
+    auto& c = ctx();
+    for (int s = 0; s < kNumStages; ++s) {
+      if (!c.stage[s]) {
+        RGC_CUDA(cudaHostAlloc(&c.stage[s], kStageBytes, cudaHostAllocDefault));
+        RGC_CUDA(cudaEventCreateWithFlags(&c.stage_free[s], cudaEventDisableTiming));
+        RGC_CUDA(cudaEventRecord(c.stage_free[s], c.stream));
+      }
+    }
+    return RGC_OK;
+  }
+
+  static bool is_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+  }
+
+  // Pinned sources go out as ONE async DMA (caller keeps them alive until the
+  // stream is synchronised); pageable sources are memcpy'd chunk-wise into a
+  // two-deep pinned ring so the CPU copy of chunk k+1 overlaps the DMA of chunk k.
+  int copy_h2d(void* dst, const void* src, std::size_t bytes, cudaStream_t stream) {
+    if (bytes == 0) {
+      return RGC_OK;
+    }
+    if (is_pinned(src)) {
+      RGC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+      return RGC_OK;
+    }
+    RGC_TRY(ensure_stages());
+    auto&       c    = ctx();
+    std::size_t done = 0;
+    int         s    = 0;
+    while (done < bytes) {
+      const std::size_t chunk = bytes - done < kStageBytes ? bytes - done : kStageBytes;
+      RGC_CUDA(cudaEventSynchronize(c.stage_free[s]));
+      std::memcpy(c.stage[s], static_cast<const char*>(src) + done, chunk);
+      RGC_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + done, c.stage[s], chunk,
+                               cudaMemcpyHostToDevice, stream));
+      RGC_CUDA(cudaEventRecord(c.stage_free[s], stream));
+      done += chunk;
+      s = (s + 1) % kNumStages;
+    }
+    return RGC_OK;
+  }
+
+  // -------------------------------------------------------------------- NCCL
+  struct NcclApi {
+    void* handle { nullptr };
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) { nullptr };
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) { nullptr };
+    ncclResult_t (*CommDestroy)(ncclComm_t) { nullptr };
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t,
+                              ncclComm_t, cudaStream_t) { nullptr };
+    const char* (*GetErrorString)(ncclResult_t) { nullptr };
+  };
+
+  static NcclApi& nccl() {
+    static NcclApi api;
+    return api;
+  }
+
+  static int load_nccl() {
+    auto& api = nccl();
+    if (api.handle) {
+      return RGC_OK;
+    }
+    // A process that already loaded NCCL (e.g. through torch) gets that copy.
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char* nm : names) {
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) {
+        break;
+      }
+    }
+    if (!api.handle) {
+      return fail(RGC_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    }
+#define RGC_NCCL_SYM(field, sym)                                                    \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, sym));        \
+  if (!api.field) {                                                                 \
+    return fail(RGC_ERR_NCCL, "libnccl lacks symbol %s", sym);                      \
+  }
+    RGC_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+    RGC_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+    RGC_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    RGC_NCCL_SYM(AllReduce, "ncclAllReduce");
+    RGC_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef RGC_NCCL_SYM
+    return RGC_OK;
+  }
+
+#define RGC_NCCL(expr)                                                              \
+  do {                                                                              \
+    ncclResult_t rgc_nr__ = (expr);                                                 \
+    if (rgc_nr__ != ncclSuccess) {                                                  \
+      return ::rgc::fail(RGC_ERR_NCCL, "%s failed: %s", #expr,                      \
+                         ::rgc::nccl().GetErrorString(rgc_nr__));                   \
+    }                                                                               \
+  } while (0)
+
+  int allreduce_sum_f64(double* dev, std::size_t n) {
+    auto& c = ctx();
+    if (!c.nccl_comm || c.nranks <= 1 || n == 0) {
+      return RGC_OK;
+    }
+    RGC_NCCL(nccl().AllReduce(dev, dev, n, ncclFloat64, ncclSum,
+                              static_cast<ncclComm_t>(c.nccl_comm), c.stream));
+    return RGC_OK;
+  }
+
+  int allreduce_sum_u64(unsigned long long* dev, std::size_t n) {
+    auto& c = ctx();
+    if (!c.nccl_comm || c.nranks <= 1 || n == 0) {
+      return RGC_OK;
+    }
+    RGC_NCCL(nccl().AllReduce(dev, dev, n, ncclUint64, ncclSum,
+                              static_cast<ncclComm_t>(c.nccl_comm), c.stream));
+    return RGC_OK;
+  }
+
+} // namespace rgc
+
+using namespace rgc;
+
+static_assert(sizeof(ncclUniqueId) == RGC_COMM_ID_BYTES, "ncclUniqueId size");
+
+extern "C" {
+
+  // ------------------------------------------------------------------ runtime
+  const char* rgc_last_error(void) { return t_last_error.c_str(); }
+
+  int rgc_device_count(int* count) {
+    int         n   = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    if (count) {
+      *count = n;
+    }
+    return RGC_OK;
+  }
+
+  int rgc_init(int device) {
+    auto& c = ctx();
+    if (c.initialized) {
+      return RGC_OK;
+    }
+    int ndev = 0;
+    rgc_device_count(&ndev);
+    if (ndev == 0) {
+      return fail(RGC_ERR_NOT_INITIALIZED,
+                  "no CUDA device visible: ragnar_cuda has no CPU fallback");
+    }
+    if (device < 0) {
+      const char* lr = std::getenv("LOCAL_RANK");
+      device         = lr ? std::atoi(lr) % ndev : 0;
+    }
+    if (device >= ndev) {
+      return fail(RGC_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+    }
+    RGC_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RGC_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+      return fail(RGC_ERR_NOT_INITIALIZED,
+                  "device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; this library "
+                  "ships sm_100a code only",
+                  device, prop.name, prop.major, prop.minor);
+    }
+    c.device    = device;
+    c.sm_count  = prop.multiProcessorCount;
+    c.hbm_bytes = prop.totalGlobalMem;
+    RGC_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    RGC_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    for (auto& e : c.ev) {
+      RGC_CUDA(cudaEventCreate(&e));
+    }
+    c.launches    = 0;
+    c.initialized = true;
+    return RGC_OK;
+  }
+
+  int rgc_finalize(void) {
+    auto& c = ctx();
+    if (!c.initialized) {
+      return RGC_OK;
+    }
+    cudaSetDevice(c.device);
+    cudaDeviceSynchronize();
+    rgc_comm_destroy();
+    for (int s = 0; s < kNumStages; ++s) {
+      if (c.stage[s]) {
+        cudaFreeHost(c.stage[s]);
+        cudaEventDestroy(c.stage_free[s]);
+        c.stage[s]      = nullptr;
+        c.stage_free[s] = nullptr;
+      }
+    }
+    if (c.scratch) {
+      cudaFree(c.scratch);
+      c.scratch       = nullptr;
+      c.scratch_bytes = 0;
+    }
+    for (auto& e : c.ev) {
+      if (e) {
+        cudaEventDestroy(e);
+        e = nullptr;
+      }
+    }
+    cudaStreamDestroy(c.stream);
+    cudaStreamDestroy(c.copy_stream);
+    c.stream      = nullptr;
+    c.copy_stream = nullptr;
+    c.initialized = false;
+    return RGC_OK;
+  }
+
+  int rgc_is_initialized(void) { return ctx().initialized ? 1 : 0; }
+
+  int rgc_device_info(int* device, int* sm_count, size_t* hbm_bytes) {
+    RGC_REQUIRE_INIT();
+    if (device) {
+      *device = ctx().device;
+    }
+    if (sm_count) {
+      *sm_count = ctx().sm_count;
+    }
+    if (hbm_bytes) {
+      *hbm_bytes = ctx().hbm_bytes;
+    }
+    return RGC_OK;
+  }
+
+  int rgc_stream(void** stream) {
+    RGC_REQUIRE_INIT();
+    *stream = static_cast<void*>(ctx().stream);
+    return RGC_OK;
+  }
+
+  int rgc_synchronize(void) {
+    RGC_REQUIRE_INIT();
+    RGC_CUDA(cudaStreamSynchronize(ctx().copy_stream));
+    RGC_CUDA(cudaStreamSynchronize(ctx().stream));
+    return RGC_OK;
+  }
+
+  uint64_t rgc_launch_count(void) { return ctx().launches.load(); }
+
+  int rgc_last_kernel_ms(float ms[2]) {
+    ms[0] = ctx().last_ms[0];
+    ms[1] = ctx().last_ms[1];
+    return RGC_OK;
+  }
+
+  int rgc_host_alloc(size_t bytes, void** ptr) {
+    RGC_REQUIRE_INIT();
+    cudaError_t err = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      return fail(RGC_ERR_OOM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(err));
+    }
+    return RGC_OK;
+  }
+
+  int rgc_host_free(void* ptr) {
+    if (ptr) {
+      RGC_CUDA(cudaFreeHost(ptr));
+    }
+    return RGC_OK;
+  }
+
+  // --------------------------------------------------------------------- comm
+  int rgc_comm_get_unique_id(unsigned char id[RGC_COMM_ID_BYTES]) {
+    RGC_TRY(load_nccl());
+    ncclUniqueId uid;
+    RGC_NCCL(nccl().GetUniqueId(&uid));
+    std::memcpy(id, &uid, RGC_COMM_ID_BYTES);
+    return RGC_OK;
+  }
+
+  int rgc_comm_init(const unsigned char id[RGC_COMM_ID_BYTES], int rank, int nranks) {
+    RGC_REQUIRE_INIT();
+    if (nranks < 1 || rank < 0 || rank >= nranks) {
+      return fail(RGC_ERR_INVALID, "bad rank %d / nranks %d", rank, nranks);
+    }
+    RGC_TRY(load_nccl());
+    auto& c = ctx();
+    if (c.nccl_comm) {
+      return fail(RGC_ERR_INVALID, "communicator already initialised");
+    }
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, RGC_COMM_ID_BYTES);
+    ncclComm_t comm = nullptr;
+    RGC_CUDA(cudaSetDevice(c.device));
+    RGC_NCCL(nccl().CommInitRank(&comm, nranks, uid, rank));
+    c.nccl_comm = comm;
+    c.rank      = rank;
+    c.nranks    = nranks;
+    return RGC_OK;
+  }
+
+  int rgc_comm_destroy(void) {
+    auto& c = ctx();
+    if (c.nccl_comm) {
+      nccl().CommDestroy(static_cast<ncclComm_t>(c.nccl_comm));
+      c.nccl_comm = nullptr;
+    }
+    c.rank   = 0;
+    c.nranks = 1;
+    return RGC_OK;
+  }
+
+  int rgc_comm_info(int* rank, int* nranks) {
+    if (rank) {
+      *rank = ctx().rank;
+    }
+    if (nranks) {
+      *nranks = ctx().nranks;
+    }
+    return RGC_OK;
+  }
+
+  // ------------------------------------------------------------------ buffers
+  int rgc_buf_create(int dtype, size_t n, rgc_buf_t** out) {
+    RGC_REQUIRE_INIT();
+    if (dtype != RGC_I32 && dtype != RGC_F32 && dtype != RGC_F64) {
+      return fail(RGC_ERR_INVALID, "unknown dtype %d", dtype);
+    }
+    auto* b = new (std::nothrow) rgc_buf;
+    if (!b) {
+      return fail(RGC_ERR_OOM, "out of host memory");
+    }
+    b->dtype = dtype;
+    b->n     = n;
+    if (n > 0) {
+      const std::size_t bytes = n * dtype_size(dtype);
+      cudaError_t       err   = cudaMalloc(&b->dev, bytes);
+      if (err != cudaSuccess) {
+        cudaGetLastError();
+        delete b;
+        return fail(RGC_ERR_OOM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(err));
+      }
+      err = cudaMemsetAsync(b->dev, 0, bytes, ctx().stream);
+      if (err != cudaSuccess) {
+        cudaFree(b->dev);
+        delete b;
+        return fail(RGC_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(err));
+      }
+    }
+    *out = b;
+    return RGC_OK;
+  }
+
+  int rgc_buf_from_host(int dtype, const void* host, size_t n, rgc_buf_t** out) {
+    rgc_buf_t* b = nullptr;
+    RGC_TRY(rgc_buf_create(dtype, n, &b));
+    if (n > 0) {
+      int rc = copy_h2d(b->dev, host, n * dtype_size(dtype), ctx().stream);
+      if (rc == RGC_OK) {
+        cudaError_t err = cudaStreamSynchronize(ctx().stream);
+        if (err != cudaSuccess) {
+          rc = fail(RGC_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(err));
+        }
+      }
+      if (rc != RGC_OK) {
+        rgc_buf_release(b);
+        return rc;
+      }
+    }
+    *out = b;
+    return RGC_OK;
+  }
+
+  int rgc_buf_to_host(const rgc_buf_t* buf, size_t start, size_t n, void* host) {
+    RGC_REQUIRE_INIT();
+    if (!buf || start + n > buf->n) {
+      return fail(RGC_ERR_INVALID, "rgc_buf_to_host: range [%zu, %zu) exceeds extent %zu",
+                  start, start + n, buf ? buf->n : (size_t)0);
+    }
+    if (n == 0) {
+      return RGC_OK;
+    }
+    const std::size_t es = dtype_size(buf->dtype);
+    RGC_CUDA(cudaMemcpyAsync(host, static_cast<const char*>(buf->dev) + start * es, n * es,
+                             cudaMemcpyDeviceToHost, ctx().stream));
+    RGC_CUDA(cudaStreamSynchronize(ctx().stream));
+    return RGC_OK;
+  }
+
+  size_t rgc_buf_size(const rgc_buf_t* buf) { return buf ? buf->n : 0; }
+  int    rgc_buf_dtype(const rgc_buf_t* buf) { return buf ? buf->dtype : -1; }
+  void*  rgc_buf_device_ptr(const rgc_buf_t* buf) { return buf ? buf->dev : nullptr; }
+
+  int rgc_buf_retain(rgc_buf_t* buf) {
+    if (buf) {
+      buf->refcount.fetch_add(1);
+    }
+    return RGC_OK;
+  }
+
+  int rgc_buf_release(rgc_buf_t* buf) {
+    if (buf && buf->refcount.fetch_sub(1) == 1) {
+      if (buf->dev && ctx().initialized) {
+        cudaStreamSynchronize(ctx().stream);
+        cudaFree(buf->dev);
+      }
+      delete buf;
+    }
+    return RGC_OK;
+  }
+
+  // ---------------------------------------------------------------- particles
+  int rgc_particles_create(int dim, rgc_particles_t** out) {
+    if (dim < 1 || dim > 3) {
+      return fail(RGC_ERR_INVALID, "dim must be 1, 2 or 3 (got %d)", dim);
+    }
+    auto* p = new (std::nothrow) rgc_particles;
+    if (!p) {
+      return fail(RGC_ERR_OOM, "out of host memory");
+    }
+    p->dim = dim;
+    *out   = p;
+    return RGC_OK;
+  }
+
+  static void free_columns(rgc_particles_t* p) {
+    for (auto& q : p->col) {
+      for (auto& c : q) {
+        if (c) {
+          cudaFree(c);
+          c = nullptr;
+        }
+      }
+    }
+  }
+
+  int rgc_particles_release(rgc_particles_t* p) {
+    if (p) {
+      if (ctx().initialized) {
+        cudaStreamSynchronize(ctx().copy_stream);
+        cudaStreamSynchronize(ctx().stream);
+        free_columns(p);
+      }
+      delete p;
+    }
+    return RGC_OK;
+  }
+
+  static std::size_t pitch_for(std::size_t nalloc) {
+    const std::size_t n = nalloc < 64 ? 64 : nalloc;
+    return (n + 63) & ~std::size_t(63);
+  }
+
+  static int alloc_column(float** col, std::size_t pitch) {
+    cudaError_t err = cudaMalloc(col, pitch * sizeof(float));
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      *col = nullptr;
+      return fail(RGC_ERR_OOM, "cudaMalloc of a %zu-particle column failed: %s", pitch,
+                  cudaGetErrorString(err));
+    }
+    RGC_CUDA(cudaMemsetAsync(*col, 0, pitch * sizeof(float), ctx().stream));
+    return RGC_OK;
+  }
+
+  int rgc_particles_allocate(rgc_particles_t* p, size_t nalloc, int with_coords) {
+    RGC_REQUIRE_INIT();
+    if (!p) {
+      return fail(RGC_ERR_INVALID, "null particles handle");
+    }
+    if (p->allocated) {
+      return fail(RGC_ERR_INVALID, "Particles already allocated");
+    }
+    p->pitch = pitch_for(nalloc);
+    for (int q = with_coords ? RGC_Q_X : RGC_Q_U; q <= RGC_Q_B; ++q) {
+      const int ncomp = q == RGC_Q_X ? p->dim : 3;
+      for (int c = 0; c < ncomp; ++c) {
+        int rc = alloc_column(&p->col[q][c], p->pitch);
+        if (rc != RGC_OK) {
+          free_columns(p);
+          return rc;
+        }
+      }
+    }
+    p->nalloc      = nalloc;
+    p->with_coords = with_coords != 0;
+    p->allocated   = true;
+    return RGC_OK;
+  }
+
+  int rgc_particles_enable_coords(rgc_particles_t* p) {
+    RGC_REQUIRE_INIT();
+    if (!p || !p->allocated) {
+      return fail(RGC_ERR_INVALID, "Particles not allocated");
+    }
+    if (p->with_coords) {
+      return RGC_OK;
+    }
+    for (int c = 0; c < p->dim; ++c) {
+      RGC_TRY(alloc_column(&p->col[RGC_Q_X][c], p->pitch));
+    }
+    p->with_coords = true;
+    return RGC_OK;
+  }
+
+  int rgc_particles_reallocate(rgc_particles_t* p, size_t nalloc) {
+    RGC_REQUIRE_INIT();
+    if (!p || !p->allocated) {
+      return fail(RGC_ERR_INVALID,
+                  "Particles not allocated, if you want to allocate, call `allocate` instead");
+    }
+    if (nalloc <= p->nalloc) {
+      return fail(RGC_ERR_INVALID, "New allocation size must be greater than the current one");
+    }
+    const std::size_t new_pitch = pitch_for(nalloc);
+    if (new_pitch > p->pitch) {
+      RGC_CUDA(cudaStreamSynchronize(ctx().copy_stream));
+      for (auto& q : p->col) {
+        for (auto& c : q) {
+          if (!c) {
+            continue;
+          }
+          float* bigger = nullptr;
+          RGC_TRY(alloc_column(&bigger, new_pitch));
+          RGC_CUDA(cudaMemcpyAsync(bigger, c, p->nalloc * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, ctx().stream));
+          RGC_CUDA(cudaStreamSynchronize(ctx().stream));
+          RGC_CUDA(cudaFree(c));
+          c = bigger;
+        }
+      }
+      p->pitch = new_pitch;
+    }
+    p->nalloc = nalloc;
+    return RGC_OK;
+  }
+
+  int    rgc_particles_has_coords(const rgc_particles_t* p) { return p && p->with_coords; }
+  size_t rgc_particles_nalloc(const rgc_particles_t* p) { return p ? p->nalloc : 0; }
+  int    rgc_particles_dim(const rgc_particles_t* p) { return p ? p->dim : 0; }
+
+  static int check_column(const rgc_particles_t* p, int quantity, int comp) {
+    if (!p || !p->allocated) {
+      return fail(RGC_ERR_INVALID, "Particles not allocated");
+    }
+    if (quantity < RGC_Q_X || quantity > RGC_Q_B) {
+      return fail(RGC_ERR_INVALID, "Invalid quantity");
+    }
+    const int ncomp = quantity == RGC_Q_X ? p->dim : 3;
+    if (comp < 0 || comp >= ncomp) {
+      return fail(RGC_ERR_INVALID, "Invalid component");
+    }
+    if (quantity == RGC_Q_X && !p->with_coords) {
+      return fail(RGC_ERR_INVALID, "Particle coordinates ignored");
+    }
+    return RGC_OK;
+  }
+
+  int rgc_particles_write(rgc_particles_t* p, int quantity, int comp, size_t start,
+                          const float* host, size_t n) {
+    RGC_REQUIRE_INIT();
+    RGC_TRY(check_column(p, quantity, comp));
+    if (start + n > p->nalloc) {
+      return fail(RGC_ERR_INVALID, "write [%zu, %zu) exceeds allocation %zu", start, start + n,
+                  p->nalloc);
+    }
+    // ordered after the zero-fill issued on the compute stream
+    return copy_h2d(p->col[quantity][comp] + start, host, n * sizeof(float), ctx().stream);
+  }
+
+  int rgc_particles_read(const rgc_particles_t* p, int quantity, int comp, size_t start,
+                         size_t n, float* host) {
+    RGC_REQUIRE_INIT();
+    RGC_TRY(check_column(p, quantity, comp));
+    if (start + n > p->nalloc) {
+      return fail(RGC_ERR_INVALID, "read [%zu, %zu) exceeds allocation %zu", start, start + n,
+                  p->nalloc);
+    }
+    if (n == 0) {
+      return RGC_OK;
+    }
+    RGC_CUDA(cudaMemcpyAsync(host, p->col[quantity][comp] + start, n * sizeof(float),
+                             cudaMemcpyDeviceToHost, ctx().stream));
+    RGC_CUDA(cudaStreamSynchronize(ctx().stream));
+    return RGC_OK;
+  }
+
+  int rgc_particles_column(const rgc_particles_t* p, int quantity, int comp, size_t n,
+                           rgc_buf_t** out) {
+    RGC_REQUIRE_INIT();
+    RGC_TRY(check_column(p, quantity, comp));
+    if (n > p->nalloc) {
+      return fail(RGC_ERR_INVALID, "column length %zu exceeds allocation %zu", n, p->nalloc);
+    }
+    rgc_buf_t* b = nullptr;
+    RGC_TRY(rgc_buf_create(RGC_F32, n, &b));
+    if (n > 0) {
+      cudaError_t err = cudaMemcpyAsync(b->dev, p->col[quantity][comp], n * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, ctx().stream);
+      if (err != cudaSuccess) {
+        rgc_buf_release(b);
+        return fail(RGC_ERR_CUDA, "cudaMemcpyAsync D2D failed: %s", cudaGetErrorString(err));
+      }
+    }
+    *out = b;
+    return RGC_OK;
+  }
+
+  void* rgc_particles_device_ptr(const rgc_particles_t* p, int quantity, int comp) {
+    if (check_column(p, quantity, comp) != RGC_OK) {
+      return nullptr;
+    }
+    return p->col[quantity][comp];
+  }
+
+} // extern "C"

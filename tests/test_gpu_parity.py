@@ -1,0 +1,190 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the
+CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): histogram counts bit-exact; spectra and weighted
+histograms within 1e-5 relative per bin of the reference's float terms summed in
+double (oracle 'f64' outputs == oracle/_ref ragnar_ref64)."""
+import numpy as np
+import pytest
+
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+SPEC_RTOL = 1e-5  # per-bin, on bins >= 1e-6 * max
+HIST_RTOL = 1e-5
+
+
+def _particles(cabi, U, E=None, B=None):
+    return cabi.Particles(3).from_columns(U=U, E=E, B=B)
+
+
+@pytest.mark.parametrize("fourvel", [True, False])
+@pytest.mark.parametrize("n", [1, 7, 1000, 2_000_003])
+def test_histogram_counts_bit_exact(cabi, port, fourvel, n):
+    U = synth.config2(n)
+    bins = cabi.logspace(1e-2, 1e3, 200)
+    p = _particles(cabi, U)
+    hist, counts, _ = cabi.energy_histogram(p, bins, log_spaced=False, fourvel=fourvel)
+    _, _, want = port.energy_distribution(*U, bins, log_spaced=False, fourvel=fourvel)
+    assert counts.sum() == n
+    assert np.array_equal(counts, want)
+    assert np.array_equal(hist, want.astype(np.float32))
+
+
+@pytest.mark.parametrize("fourvel", [True, False])
+def test_histogram_weighted(cabi, port, fourvel):
+    n = 1_000_000
+    U = synth.config2(n, seed=7)
+    bins = cabi.logspace(1e-2, 1e3, 200)
+    p = _particles(cabi, U)
+    hist, counts, s64 = cabi.energy_histogram(p, bins, log_spaced=True, fourvel=fourvel)
+    _, want64, want_counts = port.energy_distribution(*U, bins, log_spaced=True, fourvel=fourvel)
+    assert np.array_equal(counts, want_counts)
+    nz = want64 > 0
+    assert np.all(s64[~nz] == 0)
+    assert np.max(np.abs(s64[nz] - want64[nz]) / want64[nz]) < HIST_RTOL
+    assert np.allclose(hist, want64.astype(np.float32), rtol=HIST_RTOL, atol=0)
+
+
+def test_histogram_linbins_and_gamma_bins(cabi, port):
+    """index formula is logarithmic even for Linbins (reference particles.cpp:239-242)"""
+    n = 300_000
+    U = synth.config2(n, seed=11, umin=0.05, umax=50)
+    p = _particles(cabi, U)
+    for bins, fourvel in ((cabi.linspace(0.5, 40, 64), True), (cabi.logspace(1, 60, 33), False)):
+        _, counts, _ = cabi.energy_histogram(p, bins, log_spaced=False, fourvel=fourvel)
+        _, _, want = port.energy_distribution(*U, bins, log_spaced=False, fourvel=fourvel)
+        assert np.array_equal(counts, want)
+
+
+def test_histogram_edge_values(cabi, port):
+    """the survey's probe vector: values on / around the clamps"""
+    u = np.array([0.001, 0.5, 1, 5, 999, 1000, 5000, 0.0099999, 0.0], np.float32)
+    z = np.zeros_like(u)
+    bins = cabi.logspace(1e-2, 1e3, 6)
+    p = _particles(cabi, [u, z, z])
+    _, counts, _ = cabi.energy_histogram(p, bins, log_spaced=False)
+    _, _, want = port.energy_distribution(u, z, z, bins, log_spaced=False)
+    assert np.array_equal(counts, want)
+    # nactive smaller than the allocation: only the active range is binned
+    _, counts5, _ = cabi.energy_histogram(p, bins, log_spaced=False, nactive=5)
+    _, _, want5 = port.energy_distribution(u[:5], z[:5], z[:5], bins, log_spaced=False)
+    assert np.array_equal(counts5, want5)
+
+
+@pytest.mark.parametrize("maker,consts", [
+    (synth.config3, (1.0, 1.0, 1.0)),
+    (synth.full3d, (1.3, 2.0, 0.7)),
+    # production-like constants (reference legacy/simulation.cpp.bak:110-118,133-136)
+    (synth.full3d, (0.45**2 * 10 / 2, 50.0, (27 / 8) * 0.1 * 137)),
+])
+@pytest.mark.parametrize("nbins,lo,hi", [(200, 0.01, 1e5), (1000, 1e-3, 1e6), (37, 1e-3, 1e3)])
+def test_spectrum_particles(cabi, port, maker, consts, nbins, lo, hi):
+    n = 100_000 if nbins <= 200 else 30_000
+    U, E, B = maker(n)
+    bins = cabi.logspace(lo, hi, nbins)
+    p = _particles(cabi, U, E, B)
+    s32, s64 = cabi.sync_spectrum_particles(p, bins, *consts)
+    _, want = port.sync_spectrum_particles(U, E, B, bins, *consts)
+    assert want.max() > 0
+    assert synth.rel_err(s64, want) < SPEC_RTOL
+    assert np.all(s64[want == 0] == 0), "bins the reference leaves at zero must stay zero"
+    assert np.allclose(s32, s64.astype(np.float32), rtol=1e-7, atol=0)
+
+
+@pytest.mark.parametrize("n", [1, 3, 1023, 1024, 1025, 4099])
+def test_spectrum_ragged_sizes(cabi, port, n):
+    U, E, B = synth.full3d(n, seed=n)
+    bins = cabi.logspace(0.01, 1e5, 200)
+    p = _particles(cabi, U, E, B)
+    _, s64 = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)
+    _, want = port.sync_spectrum_particles(U, E, B, bins, 1.0, 1.0, 1.0)
+    assert synth.rel_err(s64, want) < SPEC_RTOL
+
+
+def test_spectrum_degenerate_particles(cabi, port):
+    """u = 0, B = 0, E-dominated (negative radicand -> NaN -> skipped), huge gamma"""
+    U = [np.array([0, 0, 1e4, 3, 0.1, 1e-3], np.float32), np.zeros(6, np.float32),
+         np.array([0, 2, 0, 4, 0, 0], np.float32)]
+    E = [np.array([0, 0, 0, 5, 0, 0], np.float32), np.zeros(6, np.float32),
+         np.array([0, 0, 0, 5, 0, 0], np.float32)]
+    B = [np.array([1, 0, 1, 0.1, 1, 1], np.float32), np.array([0, 0, 1, 0, 0, 0], np.float32),
+         np.zeros(6, np.float32)]
+    bins = cabi.logspace(1e-4, 1e9, 300)
+    p = _particles(cabi, U, E, B)
+    _, s64 = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)
+    _, want = port.sync_spectrum_particles(U, E, B, bins, 1.0, 1.0, 1.0)
+    assert np.all(np.isfinite(s64))
+    assert synth.rel_err(s64, want) < SPEC_RTOL
+
+
+def test_spectrum_unsorted_and_invalid_bins(cabi, port):
+    U, E, B = synth.config3(20_000)
+    rng = np.random.default_rng(3)
+    bins = rng.permutation(cabi.logspace(0.01, 1e5, 100)).astype(np.float32)
+    bins[5] = 0.0
+    bins[17] = -3.0
+    p = _particles(cabi, U, E, B)
+    _, s64 = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)
+    _, want = port.sync_spectrum_particles(U, E, B, bins, 1.0, 1.0, 1.0)
+    assert s64[5] == 0 and s64[17] == 0
+    assert synth.rel_err(s64, want) < SPEC_RTOL
+
+
+@pytest.mark.parametrize("case", ["config1", "sync_log", "sync_lin"])
+def test_spectrum_from_dist(cabi, port, case):
+    if case == "config1":  # BASELINE config 1 / reference README.md:47-60
+        gb = cabi.logspace(1, 100, 200)
+        f = cabi.generator_eval(0, [-2, 1, 100], gb)
+        bins, islog = cabi.logspace(0.01, 1e7, 200), True
+    elif case == "sync_log":  # reference src/tests/synchrotron.py:14-35
+        gb = cabi.logspace(1, 1000, 200)
+        f = cabi.generator_eval(0, [-2.23, 1, 1000], gb)
+        bins, islog = cabi.logspace(0.01, 1e7, 200), True
+    else:  # reference src/tests/synchrotron.py:38-59
+        gb = cabi.linspace(1, 1000, 10000)
+        f = cabi.generator_eval(0, [-2.5, 1, 1000], gb)
+        bins, islog = cabi.logspace(0.01, 1e6, 500), False
+    s32, s64 = cabi.sync_spectrum_dist(gb, f, islog, bins, 1.0, 1.0)
+    _, want = port.sync_spectrum_dist(gb, f, islog, bins, 1.0, 1.0)
+    assert synth.rel_err(s64, want) < SPEC_RTOL
+    assert np.all(s64[want == 0] == 0)
+
+
+def test_device_generator_sharding_and_additivity(cabi, port):
+    """Philox particles depend only on (seed, global index): a 2-way split of the
+    index range reproduces the single-range spectrum (fp64 round-off) and counts."""
+    n = 200_000
+    bins = cabi.logspace(1e-3, 1e6, 1000)
+    gbins = cabi.logspace(1e-2, 1e3, 200)
+    whole = cabi.Particles(3).allocate(n).generate(1, 42, 0, 0, n, 0.05, 500.0)
+    _, s_whole = cabi.sync_spectrum_particles(whole, bins, 1.0, 1.0, 1.0)
+    _, c_whole, _ = cabi.energy_histogram(whole, gbins, False)
+    parts, cparts = np.zeros_like(s_whole), np.zeros_like(c_whole)
+    for off, cnt in ((0, 70_001), (70_001, n - 70_001)):
+        shard = cabi.Particles(3).allocate(cnt).generate(1, 42, off, 0, cnt, 0.05, 500.0)
+        parts += cabi.sync_spectrum_particles(shard, bins, 1.0, 1.0, 1.0)[1]
+        cparts += cabi.energy_histogram(shard, gbins, False)[1]
+        # shard data are bit-identical to the matching slice of the whole
+        for q in (cabi.Q_U, cabi.Q_E, cabi.Q_B):
+            for d in range(3):
+                assert np.array_equal(shard.read(q, d, 0, cnt), whole.read(q, d, off, cnt))
+    assert np.array_equal(cparts, c_whole)
+    assert np.allclose(parts, s_whole, rtol=1e-12, atol=0)
+    # and the device-generated sample agrees with the oracle
+    cols = [[whole.read(q, d, 0, 20_000) for d in range(3)] for q in (cabi.Q_U, cabi.Q_E, cabi.Q_B)]
+    sub = cabi.Particles(3).from_columns(*cols)
+    _, s_sub = cabi.sync_spectrum_particles(sub, bins, 1.0, 1.0, 1.0)
+    _, want = port.sync_spectrum_particles(*cols, bins, 1.0, 1.0, 1.0)
+    assert synth.rel_err(s_sub, want) < SPEC_RTOL
+
+
+def test_repeatable(cabi):
+    U, E, B = synth.full3d(50_000)
+    bins = cabi.logspace(0.01, 1e5, 200)
+    p = _particles(cabi, U, E, B)
+    a = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)[1]
+    b = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)[1]
+    assert np.array_equal(a, b), "fixed-order reductions: bitwise reproducible"
+    assert cabi.launch_count() > 0
