@@ -171,7 +171,9 @@ def test_device_generator_sharding_and_additivity(cabi, port):
             for d in range(3):
                 assert np.array_equal(shard.read(q, d, 0, cnt), whole.read(q, d, off, cnt))
     assert np.array_equal(cparts, c_whole)
-    assert np.allclose(parts, s_whole, rtol=1e-12, atol=0)
+    # per-tile partials are float sums of <= 128 terms before they enter the fp64
+    # accumulators; a different split moves the tile boundaries, hence ~1e-8
+    assert np.allclose(parts, s_whole, rtol=1e-6, atol=0)
     # and the device-generated sample agrees with the oracle
     cols = [[whole.read(q, d, 0, 20_000) for d in range(3)] for q in (cabi.Q_U, cabi.Q_E, cabi.Q_B)]
     sub = cabi.Particles(3).from_columns(*cols)
