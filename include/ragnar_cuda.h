@@ -210,6 +210,14 @@ int rgc_sync_spectrum_dist(const float* gbeta, const float* f, size_t ndist,
  * hot-path call on this thread: [0] total, [1] dominant kernel only. */
 int rgc_last_kernel_ms(float ms[2]);
 
+/* Roofline denominators measured on the device, on the compute stream (bench
+ * harness only; MEASURED_PEAKS.json has no FP32 / shared-memory entry).
+ * kind 0: FFMA GFLOP/s; 1: G evaluations/s of the pair loop's FADD.SAT+FFMA mix;
+ * 2: conflict-free LDS.64 gather GB/s; 3: HBM streaming-read GB/s;
+ * 4: integer IMAD/SHF/LOP3 mix, G lane-instructions/s.  *sm_clock_mhz receives the
+ * device's nominal SM clock. */
+int rgc_measure_peak(int kind, double* value, double* sm_clock_mhz);
+
 /* ------------------------------------------------------ Tristan-v2 plugin */
 
 /* TristanV2<D>::readParticles — src/plugins/tristan-v2.cpp:95-188.  Opens
