@@ -103,6 +103,27 @@ namespace rgc {
                                     float energy_max, std::size_t n);
   double      host_energy_from_usqr(float Usqr, bool fourvel);
 
+  // ------------------------------------------------- synchrotron table plan
+  // The F(x) table as the kernels see it: node positions in cell units of the
+  // uniform log grid the reference indexes with (tabulation.hpp:33-35).
+  struct TablePlan {
+    double              L0 { 0 }, dL { 0 };
+    std::vector<double> tx; // actual node positions in cell units
+    std::vector<double> y;
+    std::size_t         T { 0 };
+  };
+
+} // namespace rgc
+
+struct rgc_particles;
+
+namespace rgc {
+  // bucketed hinge path (rgc_sync_pair.cu)
+  bool pair_path_eligible(const TablePlan& tp, const float* bins_e_syn,
+                          const std::vector<int>& bins);
+  int  run_spectrum_pair(const rgc_particles* prtls, std::size_t n, float B0, float g_syn,
+                         float e_at, const TablePlan& tp, const float* bins_e_syn,
+                         const std::vector<int>& bins, std::vector<double>& acc, float* main_ms);
 } // namespace rgc
 
 // ------------------------------------------------------------ opaque handles

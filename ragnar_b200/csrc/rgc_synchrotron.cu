@@ -44,6 +44,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -293,13 +294,6 @@ namespace rgc {
   }
 
   // ------------------------------------------------------------------ host side
-  struct TablePlan {
-    double               L0 { 0 }, dL { 0 };
-    std::vector<double>  tx;    // actual node positions in cell units
-    std::vector<double>  y;
-    std::size_t          T { 0 };
-  };
-
   static int make_table_plan(const float* tab_x, const float* tab_y, std::size_t T,
                              TablePlan& tp) {
     if (T < 2) {
@@ -478,6 +472,28 @@ namespace rgc {
     chunk_bins(tp, bins_e_syn, nbins, chunks, nan_bins);
 
     acc_host.assign(nbins, 0.0);
+    RGC_CUDA(cudaEventRecord(c.ev[0], c.stream));
+    float main_ms = 0.f;
+    // ---- bucketed hinge path (rgc_sync_pair.cu) for every chunk it can take;
+    // RGC_SPECTRUM_PATH=gather forces the gather kernel below (A/B checks)
+    if (!from_dist) {
+      const char* force = std::getenv("RGC_SPECTRUM_PATH");
+      const bool  allow = !(force && std::strcmp(force, "gather") == 0);
+      std::vector<std::vector<int>> rest;
+      for (auto& chunk : chunks) {
+        if (allow && pair_path_eligible(tp, bins_e_syn, chunk)) {
+          std::vector<double> acc;
+          RGC_TRY(run_spectrum_pair(src.prtls, src.n, src.B0, src.g_syn, src.e_at, tp, bins_e_syn,
+                                    chunk, acc, &main_ms));
+          for (std::size_t s = 0; s < chunk.size(); ++s) {
+            acc_host[chunk[s]] = acc[s];
+          }
+        } else {
+          rest.push_back(std::move(chunk));
+        }
+      }
+      chunks.swap(rest);
+    }
     // device scratch: acc64[nbins] | per launch: a_fx, table, partials
     const int ctas_per_sm = 2;
     const std::size_t ntiles = (src.n + kTile - 1) / kTile;
@@ -507,8 +523,6 @@ namespace rgc {
     double* d_part  = reinterpret_cast<double*>(sbase + off_part);
 
     RGC_CUDA(cudaMemsetAsync(d_acc, 0, nbins * sizeof(double), c.stream));
-    RGC_CUDA(cudaEventRecord(c.ev[0], c.stream));
-    float main_ms = 0.f;
     std::vector<double> out_host;
     for (std::size_t k = 0; k < plans.size(); ++k) {
       const LaunchPlan& lp = plans[k];

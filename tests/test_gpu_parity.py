@@ -190,3 +190,21 @@ def test_repeatable(cabi):
     b = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)[1]
     assert np.array_equal(a, b), "fixed-order reductions: bitwise reproducible"
     assert cabi.launch_count() > 0
+
+
+@pytest.mark.parametrize("nbins,lo,hi", [(200, 0.01, 1e5), (1000, 1e-3, 1e6), (5, 1.0, 10.0),
+                                          (254, 1e-2, 1e4), (255, 1e-2, 1e4)])
+def test_spectrum_pair_path_matches_gather_path(cabi, port, nbins, lo, hi, monkeypatch):
+    """the bucketed hinge kernel (default) and the gather kernel are two
+    formulations of the same sum: they must agree far inside the parity bar"""
+    U, E, B = synth.full3d(60_000, seed=5)
+    bins = cabi.logspace(lo, hi, nbins)
+    p = _particles(cabi, U, E, B)
+    monkeypatch.setenv("RGC_SPECTRUM_PATH", "gather")
+    _, gather = cabi.sync_spectrum_particles(p, bins, 1.0, 2.0, 3.0)
+    monkeypatch.delenv("RGC_SPECTRUM_PATH")
+    _, pair = cabi.sync_spectrum_particles(p, bins, 1.0, 2.0, 3.0)
+    _, want = port.sync_spectrum_particles(U, E, B, bins, 1.0, 2.0, 3.0)
+    assert synth.rel_err(pair, gather) < 2e-6
+    assert synth.rel_err(pair, want) < SPEC_RTOL
+    assert np.all(pair[want == 0] == 0)
