@@ -209,6 +209,9 @@ int rgc_sync_spectrum_dist(const float* gbeta, const float* f, size_t ndist,
 /* Device time (ms, CUDA events on the compute stream) of the kernels of the last
  * hot-path call on this thread: [0] total, [1] dominant kernel only. */
 int rgc_last_kernel_ms(float ms[2]);
+/* same, up to n = 4 entries: [2] the per-particle prologue kernel of the spectrum
+ * (sync_prologue_kernel), [3] reserved */
+int rgc_last_kernel_times(float* ms, int n);
 
 /* Roofline denominators measured on the device, on the compute stream (bench
  * harness only; MEASURED_PEAKS.json has no FP32 / shared-memory entry).

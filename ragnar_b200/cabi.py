@@ -74,6 +74,7 @@ SIGNATURES = {
     "rgc_sync_spectrum_dist": (C.c_int, [_f32p, _f32p, _sz, C.c_int, _f32p, _sz, _f32p, _f32p,
                                          _sz, C.c_float, C.c_float, _f32p, _f64p]),
     "rgc_last_kernel_ms": (C.c_int, [_f32p]),
+    "rgc_last_kernel_times": (C.c_int, [_f32p, C.c_int]),
     "rgc_measure_peak": (C.c_int, [C.c_int, _f64p, _f64p]),
     "rgc_tristan_read_particles": (C.c_int, [C.c_char_p, _sz, C.c_uint, _sz, _sz, _sz, C.c_int,
                                              C.c_int, _vpp, C.POINTER(_sz), C.POINTER(_sz)]),
@@ -158,6 +159,13 @@ def last_kernel_ms():
     ms = (C.c_float * 2)()
     check(lib().rgc_last_kernel_ms(ms))
     return float(ms[0]), float(ms[1])
+
+
+def last_kernel_times():
+    """(total, dominant kernel, prologue kernel, reserved) of the last hot-path call, ms"""
+    ms = (C.c_float * 4)()
+    check(lib().rgc_last_kernel_times(ms, 4))
+    return tuple(float(x) for x in ms)
 
 
 PEAK_FFMA, PEAK_PAIR, PEAK_LDS64, PEAK_HBM_READ, PEAK_INT = range(5)

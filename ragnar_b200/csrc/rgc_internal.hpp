@@ -64,8 +64,8 @@ namespace rgc {
     void*       stage[kNumStages] { nullptr, nullptr };
     cudaEvent_t stage_free[kNumStages] { nullptr, nullptr };
     // event pair for rgc_last_kernel_ms
-    cudaEvent_t ev[4] { nullptr, nullptr, nullptr, nullptr };
-    float       last_ms[2] { 0.f, 0.f };
+    cudaEvent_t ev[6] { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    float       last_ms[4] { 0.f, 0.f, 0.f, 0.f }; // total, dominant kernel, prologue kernel, -
     // NCCL (dlopen'ed lazily)
     void* nccl_comm { nullptr };
     int   rank { 0 };

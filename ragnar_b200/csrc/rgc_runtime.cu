@@ -319,6 +319,13 @@ extern "C" {
     return RGC_OK;
   }
 
+  int rgc_last_kernel_times(float* ms, int n) {
+    for (int i = 0; i < n; ++i) {
+      ms[i] = i < 4 ? ctx().last_ms[i] : 0.f;
+    }
+    return RGC_OK;
+  }
+
   int rgc_host_alloc(size_t bytes, void** ptr) {
     RGC_REQUIRE_INIT();
     cudaError_t err = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);

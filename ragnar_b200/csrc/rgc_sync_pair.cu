@@ -49,6 +49,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -62,7 +63,7 @@ namespace rgc {
   constexpr int kPMaxBins  = 8 * (kPMaxGPW * 32 - 2); // 2032 per launch
   constexpr int kPMaxBuckets = 1024;
   constexpr unsigned kInvalidKey = 0xffffu;
-  constexpr int kSegCost = 8; // per-segment overhead of the pair phase, in sorted entries
+  constexpr int kSegCostDefault = 16; // per-segment overhead of the pair phase, in sorted entries
 
   struct PairParams {
     const float* u[3];
@@ -74,15 +75,21 @@ namespace rgc {
     const float4* coef_dh; // per padded cell {hinge coefficient, hinge position, sign, 0}
     int n_pad, nb, nbp, ncols;
     int kmin;              // bucket = floor(c) - kmin
+    double kmin_d;
     double inv_B0;           // 1 / B0
     double e_scale;          // e_syn_at_g_syn / (g_syn * g_syn), the float product promoted
     double cells_per_octave; // log10(2) / dL
     double c0, inv_dL, c_lo, c_hi;
+    // staged per-particle results of the prologue kernel, padded to whole tiles
+    float2*         cw;   // (fc, w)
+    unsigned short* keys; // bucket, kInvalidKey = not on the table
+    std::size_t     npad; // ntiles * kPTile
     double* partials; // [cta][nslots] hinge sums
     double* moments;  // [cta][2 * nb]  S0 then S1 per bucket
     int     nslots;
+    int     seg_cost; // cost-model weight of one bucket segment, in sorted entries
     // shared-memory layout (byte offsets, computed once on the host)
-    int o_coef, o_s0tot, o_s1tot, o_start, o_cstart, o_hw, o_stage_cw, o_stage_k, o_sorted, o_edge, o_scan;
+    int o_coef, o_s0tot, o_s1tot, o_start, o_cstart, o_hw, o_stage_cw, o_stage_k, o_sorted, o_edge, o_scan, o_mbar, o_seg_s0, o_seg_s1;
   };
 
   struct PairEdge {
@@ -93,7 +100,7 @@ namespace rgc {
   __host__ __device__ inline std::size_t pair_align16(std::size_t x) { return (x + 15) & ~std::size_t(15); }
 
   struct PairSmem {
-    std::size_t coef, s0tot, s1tot, start, cstart, hw, stage_cw, stage_k, sorted, edge, scan, total;
+    std::size_t coef, s0tot, s1tot, start, cstart, seg_s0, seg_s1, hw, stage_cw, stage_k, sorted, edge, scan, mbar, total;
   };
 
   __host__ __device__ inline PairSmem pair_smem_layout(int n_pad, int nb, int nbp) {
@@ -102,117 +109,220 @@ namespace rgc {
     L.coef = o;      o = pair_align16(o + (std::size_t)n_pad * sizeof(float4));
     L.s0tot = o;     o = pair_align16(o + (std::size_t)nb * sizeof(double));
     L.s1tot = o;     o = pair_align16(o + (std::size_t)nb * sizeof(double));
-    L.start = o;     o = pair_align16(o + (std::size_t)(nb + 1) * sizeof(int));
-    L.cstart = o;    o = pair_align16(o + (std::size_t)(nb + 1) * sizeof(int));
+    L.start = o;     o = pair_align16(o + (std::size_t)(nb + 2) * sizeof(int));
+    L.cstart = o;    o = pair_align16(o + (std::size_t)(nb + 2) * sizeof(int));
+    L.seg_s0 = o;    o = pair_align16(o + (std::size_t)(nb + 2) * sizeof(float));
+    L.seg_s1 = o;    o = pair_align16(o + (std::size_t)(nb + 2) * sizeof(float));
     L.hw = o;        o = pair_align16(o + (std::size_t)kPWarps * nbp * sizeof(unsigned short));
     L.stage_cw = o;  o = pair_align16(o + (std::size_t)kPTile * sizeof(float2));
     L.stage_k = o;   o = pair_align16(o + (std::size_t)kPTile * sizeof(unsigned short));
     L.sorted = o;    o = pair_align16(o + (std::size_t)(kPTile + nb + 10) * sizeof(float2));
     L.edge = o;      o = pair_align16(o + (std::size_t)kPWarps * 2 * sizeof(PairEdge));
     L.scan = o;      o = pair_align16(o + (std::size_t)(2 * kPWarps + 1) * sizeof(int));
+    L.mbar = o;      o = pair_align16(o + 16);
     L.total = o;
     return L;
   }
 
-  // 1/sqrt(x) for x in the normal float range: MUFU.RSQ seed (2^-22) and one
-  // second-order Newton step in fp64 -> relative error ~2^-45.  The software
-  // sqrt()/division sequences this replaces cost ~10x more issue slots.
+  // The prologue is bound by the XU pipe (16 lanes/clk/SM: MUFU and every
+  // float<->double conversion), so it spends as few of those as it can: 9 input
+  // conversions, two MUFU.RSQ64H, one MUFU.RCP64H, one I2F and two results -> float.
+
+  // 1/sqrt(x), x a positive normal double: MUFU.RSQ64H seed (~2^-20) and one
+  // second-order Newton step -> relative error < 1e-12
   __device__ __forceinline__ double rsqrt_nr(double x) {
-    const double r = (double)rsqrtf((float)x);
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     const double t = x * r;
     const double e = fma(-t, r, 1.0);
     return fma(r * 0.5, e, r);
   }
 
-  // log2 of a positive normal float, |error| < 1e-9: exponent + atanh series of
+  // log2 of a positive normal double, |error| < 1e-12: exponent + atanh series of
   // the mantissa folded into [sqrt(1/2), sqrt(2)); the quotient (m-1)/(m+1) comes
-  // from a MUFU.RCP seed refined by one Newton step in fp64, the series tail
-  // (relative weight <= 0.03) is float
-  __device__ __forceinline__ double log2_pos(float x) {
-    const int bits = __float_as_int(x);
-    int       ex   = (bits >> 23) - 127;
-    float     m    = __int_as_float((bits & 0x007fffff) | 0x3f800000);
-    if (m > 1.41421356f) {
-      m *= 0.5f;
+  // from a MUFU.RCP64H seed refined by one Newton step
+  __device__ __forceinline__ double log2_pos(double x) {
+    const int hi = __double2hiint(x);
+    int       ex = ((hi >> 20) & 0x7ff) - 1023;
+    double    m  = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    if (m > 1.4142135623730951) {
+      m *= 0.5;
       ex += 1;
     }
-    const double md = (double)m;
-    const double a  = md - 1.0, b = md + 1.0;
-    double       rc = (double)__frcp_rn((float)b);
+    const double a = m - 1.0, b = m + 1.0;
+    double       rc;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(b));
     rc              = fma(rc, fma(-b, rc, 1.0), rc);
     const double s  = a * rc;
-    const float  sf = (float)s, s2 = sf * sf;
-    float        t  = fmaf(s2, 1.0f / 13.0f, 1.0f / 11.0f);
-    t               = fmaf(s2, t, 1.0f / 9.0f);
-    t               = fmaf(s2, t, 1.0f / 7.0f);
-    t               = fmaf(s2, t, 1.0f / 5.0f);
-    t               = fmaf(s2, t, 1.0f / 3.0f);
+    const double s2 = s * s; // <= 0.0295
+    double       t  = fma(s2, 1.0 / 15.0, 1.0 / 13.0);
+    t               = fma(s2, t, 1.0 / 11.0);
+    t               = fma(s2, t, 1.0 / 9.0);
+    t               = fma(s2, t, 1.0 / 7.0);
+    t               = fma(s2, t, 1.0 / 5.0);
+    t               = fma(s2, t, 1.0 / 3.0);
     t               = t * s2;
     const double sc = s * 2.8853900817779268; // 2 / ln 2
-    return (double)ex + fma(sc, (double)t, sc);
+    return (double)ex + fma(sc, t, sc);
   }
 
   // reference src/physics/synchrotron.hpp:193-231 — gamma, beta, beta.E, beta x B,
-  // chiR, e_peak — with the reference's promotions (float products, fp64 sums),
-  // rounded to float exactly where the reference rounds (chiR, e_peak); then the
-  // table coordinate of e_peak split into bucket and fraction.  The square roots,
-  // quotients and the logarithm go through rsqrt_nr / log2_pos (fp64-accurate to
-  // ~1e-13, i.e. far inside one float ulp of chiR and e_peak); arguments outside
-  // the normal float range take the exact libdevice route.
+  // chiR, e_peak — in fp64 like the reference's promoted arithmetic, then the table
+  // coordinate of e_peak split into bucket and fraction.  Two deliberate, bounded
+  // departures from the reference's rounding sequence (the gather kernel keeps the
+  // exact one; tests pin the two paths against each other):
+  //   * ux*ux etc. enter gamma^2 unrounded (the reference rounds each square to float
+  //     before promoting it), and e_peak is formed from the unrounded chiR and is not
+  //     itself rounded to float: e_peak moves by < 2 float ulp, i.e. the table
+  //     coordinate by ~1e-6 cell;
+  //   * sqrt, quotients and log10 go through rsqrt_nr / log2_pos (error < 1e-12).
+  // The weight chiR is rounded to float exactly as in the reference.
   __device__ __forceinline__ bool pair_prologue(const PairParams& P, float ux, float uy, float uz,
                                                 float ex, float ey, float ez, float bx, float by,
                                                 float bz, unsigned& bucket, float& fc, float& w) {
-    const double g2 = ((1.0 + (double)(ux * ux)) + (double)(uy * uy)) + (double)(uz * uz);
-    const bool   g_ok = g2 < 1e37;
-    const double rg   = g_ok ? rsqrt_nr(g2) : 1.0 / sqrt(g2);
-    const double beta_x = (double)ux * rg;
-    const double beta_y = (double)uy * rg;
-    const double beta_z = (double)uz * rg;
+    const double dux = (double)ux, duy = (double)uy, duz = (double)uz;
     const double dex = (double)ex, dey = (double)ey, dez = (double)ez;
     const double dbx = (double)bx, dby = (double)by, dbz = (double)bz;
+    const double g2  = fma(duz, duz, fma(duy, duy, fma(dux, dux, 1.0)));
+    const double rg  = rsqrt_nr(g2);
+    const double beta_x = dux * rg, beta_y = duy * rg, beta_z = duz * rg;
     const double bde = fma(beta_z, dez, fma(beta_y, dey, beta_x * dex));
     const double sx  = dex + fma(beta_y, dbz, -(beta_z * dby));
     const double sy  = dey + fma(beta_z, dbx, -(beta_x * dbz));
     const double sz  = dez + fma(beta_x, dby, -(beta_y * dbx));
     const double q   = fma(-bde, bde, fma(sz, sz, fma(sy, sy, sx * sx)));
-    double       root;
-    if (q > 1e-36 && q < 1e37) {
-      root = q * rsqrt_nr(q);
-    } else {
-      root = sqrt(q); // 0, NaN (negative radicand: skipped below), or out of float range
-    }
-    const float chiR   = (float)(root * P.inv_B0);
-    const float e_peak = (float)((P.e_scale * g2) * (double)chiR);
-    // reference synchrotron.hpp:162 `if (e_peak > 0.0)`; +inf passes there but
-    // gives x0 = 0 < xmin, i.e. nothing
-    if (!(e_peak > 0.0f && e_peak < __int_as_float(0x7f800000))) {
+    // q <= 0: chiR = 0 or NaN in the reference, the pair is skipped (synchrotron.hpp:162);
+    // NaN / inf inputs fail this or the range checks below
+    if (!(q > 1e-280 && q < 1e280)) {
       return false;
     }
-    double c;
-    if (e_peak >= 1.17549435e-38f) {
-      c = fma(-log2_pos(e_peak), P.cells_per_octave, P.c0);
-    } else {
-      c = P.c0 - log10((double)e_peak) * P.inv_dL;
+    const double chi = (q * rsqrt_nr(q)) * P.inv_B0;
+    const double ep  = (P.e_scale * g2) * chi;
+    // float(e_peak) must be a positive finite float (else x0 = e_syn / e_peak is
+    // off the table on either side)
+    if (!(ep > 1e-37 && ep < 3.4028234e38)) {
+      return false;
     }
+    const double c = fma(-log2_pos(ep), P.cells_per_octave, P.c0);
     if (!(c >= P.c_lo && c < P.c_hi)) {
       return false;
     }
-    const double fl = floor(c);
-    bucket = (unsigned)((int)fl - P.kmin);
+    // floor(c) without FRND / F2I: round-to-nearest of c - 1/2 through the 2^52 trick;
+    // an exact integer c may land on either neighbour, (K, fc = 0) and (K - 1, fc = 1)
+    // being the same table coordinate
+    const double magic = 6755399441055744.0; // 1.5 * 2^52
+    const double rm    = (c - 0.5) + magic;
+    int          ri    = __double2loint(rm);
+    double       fl    = rm - magic;
+    if (ri < P.kmin) {
+      ri = P.kmin;
+      fl = P.kmin_d;
+    }
+    bucket = (unsigned)(ri - P.kmin);
     fc     = (float)(c - fl);
-    w      = chiR;
+    w      = (float)chi;
     return true;
   }
 
+  // ---- TMA bulk copy + mbarrier (raw PTX; one transaction barrier per CTA)
+  __device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+  }
+  __device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  }
+  __device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+  }
+  __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+        smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+  }
+  __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    unsigned ok;
+    do {
+      asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    } while (!ok);
+  }
+
+  // Lanes holding the same 11-bit key, from 11 ballots (MATCH.ANY takes several
+  // hundred cycles when most of a warp's keys differ, which is the normal case here)
+  __device__ __forceinline__ unsigned match_key11(unsigned key) {
+    unsigned m = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < 11; ++i) {
+      const unsigned bit = (key >> i) & 1u;
+      const unsigned bal = __ballot_sync(0xffffffffu, bit != 0u);
+      m &= bit ? bal : ~bal;
+    }
+    return m;
+  }
+
+  // ---- kernel 1: per-particle prologue, streamed once over the particle columns
+  // (36 B read, 10 B written per particle; HBM-bound).  Entries past nprtl up to the
+  // end of the last tile are written as invalid so the pair kernel copies whole tiles.
+  template <int MINB>
+  __global__ void __launch_bounds__(256, MINB)
+    sync_prologue_kernel(const __grid_constant__ PairParams P) {
+    const std::size_t stride = (std::size_t)gridDim.x * blockDim.x * 4;
+    for (std::size_t i0 = ((std::size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < P.npad;
+         i0 += stride) {
+      float4 v[9];
+      if (i0 < P.nprtl) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          v[d]     = __ldcs(reinterpret_cast<const float4*>(P.u[d] + i0));
+          v[3 + d] = __ldcs(reinterpret_cast<const float4*>(P.e[d] + i0));
+          v[6 + d] = __ldcs(reinterpret_cast<const float4*>(P.b[d] + i0));
+        }
+      }
+      const float*   f = reinterpret_cast<const float*>(v);
+      float          out_cw[8];
+      unsigned short out_k[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        unsigned bucket = kInvalidKey;
+        float    fc = 0.0f, w = 0.0f;
+        bool     ok = false;
+        if (i0 + k < P.nprtl) {
+          ok = pair_prologue(P, f[0 * 4 + k], f[1 * 4 + k], f[2 * 4 + k], f[3 * 4 + k],
+                             f[4 * 4 + k], f[5 * 4 + k], f[6 * 4 + k], f[7 * 4 + k],
+                             f[8 * 4 + k], bucket, fc, w);
+        }
+        out_k[k]          = (unsigned short)(ok ? bucket : kInvalidKey);
+        out_cw[2 * k]     = ok ? fc : 0.0f;
+        out_cw[2 * k + 1] = ok ? w : 0.0f;
+      }
+      float4* cw4 = reinterpret_cast<float4*>(P.cw + i0);
+      cw4[0]      = make_float4(out_cw[0], out_cw[1], out_cw[2], out_cw[3]);
+      cw4[1]      = make_float4(out_cw[4], out_cw[5], out_cw[6], out_cw[7]);
+      *reinterpret_cast<uint2*>(P.keys + i0) =
+        make_uint2((unsigned)out_k[0] | ((unsigned)out_k[1] << 16),
+                   (unsigned)out_k[2] | ((unsigned)out_k[3] << 16));
+    }
+  }
+
+  // ---- kernel 2: bucket sort inside the tile + the pair loop
   template <int GPW>
   __global__ void __launch_bounds__(kPThreads, 2)
     sync_pair_kernel(const __grid_constant__ PairParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float4*         coef     = reinterpret_cast<float4*>(smem_raw + P.o_coef);
     double*         s0tot    = reinterpret_cast<double*>(smem_raw + P.o_s0tot);
     double*         s1tot    = reinterpret_cast<double*>(smem_raw + P.o_s1tot);
-    int*            start    = reinterpret_cast<int*>(smem_raw + P.o_start);
-    int*            cstart   = reinterpret_cast<int*>(smem_raw + P.o_cstart);
+    int*            seg_start = reinterpret_cast<int*>(smem_raw + P.o_start);   // [nb + 2]
+    int*            seg_b     = reinterpret_cast<int*>(smem_raw + P.o_cstart);  // [nb + 2]
+    float*          seg_s0    = reinterpret_cast<float*>(smem_raw + P.o_seg_s0);
+    float*          seg_s1    = reinterpret_cast<float*>(smem_raw + P.o_seg_s1);
     unsigned short* hw16     = reinterpret_cast<unsigned short*>(smem_raw + P.o_hw);
     unsigned*       hw32     = reinterpret_cast<unsigned*>(smem_raw + P.o_hw);
     float2*         stage_cw = reinterpret_cast<float2*>(smem_raw + P.o_stage_cw);
@@ -220,6 +330,7 @@ namespace rgc {
     float2*         sorted   = reinterpret_cast<float2*>(smem_raw + P.o_sorted);
     PairEdge*       edge     = reinterpret_cast<PairEdge*>(smem_raw + P.o_edge);
     int*            scan_tmp = reinterpret_cast<int*>(smem_raw + P.o_scan);
+    void*           mbar     = smem_raw + P.o_mbar;
 
     const int tid  = threadIdx.x;
     const int lane = tid & 31;
@@ -230,6 +341,21 @@ namespace rgc {
     const int nb   = P.nb;
     const int nbp  = P.nbp;
 
+    const std::size_t ntiles = P.npad / kPTile;
+    constexpr unsigned kStageBytesCW = kPTile * sizeof(float2);
+    constexpr unsigned kStageBytesK  = kPTile * sizeof(unsigned short);
+    // the staged (fc, w, key) of a tile arrive by TMA bulk copy; the copy of the next
+    // tile is issued as soon as the sort no longer reads the staging buffers, so it
+    // lands underneath the pair loop
+    auto issue_tile_copy = [&](std::size_t tile) {
+      mbar_expect_tx(mbar, kStageBytesCW + kStageBytesK);
+      bulk_g2s(stage_cw, P.cw + tile * kPTile, kStageBytesCW, mbar);
+      bulk_g2s(stage_k, P.keys + tile * kPTile, kStageBytesK, mbar);
+    };
+    if (tid == 0) {
+      mbar_init(mbar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int i = tid; i < P.n_pad; i += kPThreads) {
       coef[i] = P.coef_dh[i];
     }
@@ -239,6 +365,10 @@ namespace rgc {
     }
     if (tid < kPWarps * 2) {
       edge[tid].b = -1;
+    }
+    __syncthreads();
+    if (tid == 0 && blockIdx.x < ntiles) {
+      issue_tile_copy(blockIdx.x);
     }
 
     int    aoff[GPW];
@@ -255,55 +385,57 @@ namespace rgc {
       accd[g] = 0.0;
     }
 
-    const std::size_t ntiles = (P.nprtl + kPTile - 1) / kPTile;
-    const int         bpt    = (nb + kPThreads - 1) / kPThreads; // buckets per thread in the scan
+    const int bpt    = (nb + kPThreads - 1) / kPThreads; // buckets per thread in the scan
+    unsigned  parity = 0;
 
     for (std::size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const std::size_t base = tile * kPTile;
-      // ---- per-warp bucket counters (packed pairs of u16)
+      // ---- per-warp bucket cursors (u16), zeroed; the previous tile's pair phase is
+      // complete once every warp has passed this barrier
       for (int i = tid; i < kPWarps * nbp / 2; i += kPThreads) {
         hw32[i] = 0u;
       }
-      __syncthreads(); // also: the previous tile's pair phase is complete
-      // ---- pass 1: prologue, stage, count
-      unsigned* my_hw32 = hw32 + warp * (nbp / 2);
-#pragma unroll 1
-      for (int r = 0; r < kPSteps / 4; ++r) {
-        const std::size_t i0 = base + (std::size_t)r * (kPThreads * 4) + (std::size_t)tid * 4;
-        float4            v[9];
-        if (i0 < P.nprtl) {
+      __syncthreads();
+      mbar_wait(mbar, parity);
+      parity ^= 1u;
+      // ---- pass A: stable rank of every particle among its warp's particles of the
+      // same bucket (warp w owns tile entries [512 w, 512 w + 512), 32 per step).
+      // The lanes of a step are grouped by key (match_key11); the group's first lane
+      // advances the warp's cursor of that bucket.
+      unsigned short* cur = hw16 + warp * nbp;
+      unsigned        rank_pack[kPSteps / 2]; // u16 ranks, two per register
 #pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            v[d]     = __ldcs(reinterpret_cast<const float4*>(P.u[d] + i0));
-            v[3 + d] = __ldcs(reinterpret_cast<const float4*>(P.e[d] + i0));
-            v[6 + d] = __ldcs(reinterpret_cast<const float4*>(P.b[d] + i0));
-          }
+      for (int s4 = 0; s4 < kPSteps; s4 += 4) {
+        unsigned key[4], m[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          key[j] = stage_k[warp * (kPTile / kPWarps) + (s4 + j) * 32 + lane];
+          m[j]   = match_key11(key[j]);
         }
-        const float* f = reinterpret_cast<const float*>(v);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          unsigned bucket = kInvalidKey;
-          float    fc = 0.0f, w = 0.0f;
-          bool     ok = false;
-          if (i0 + k < P.nprtl) {
-            ok = pair_prologue(P, f[0 * 4 + k], f[1 * 4 + k], f[2 * 4 + k], f[3 * 4 + k],
-                               f[4 * 4 + k], f[5 * 4 + k], f[6 * 4 + k], f[7 * 4 + k],
-                               f[8 * 4 + k], bucket, fc, w);
+        for (int j = 0; j < 4; ++j) {
+          const bool valid = key[j] != kInvalidKey;
+          const int  lead  = __ffs(m[j]) - 1;
+          int        basev = 0;
+          if (valid && lane == lead) {
+            basev       = cur[key[j]];
+            cur[key[j]] = (unsigned short)(basev + __popc(m[j]));
           }
-          const int slot = (r * 4 + k) * kPThreads + tid;
-          stage_k[slot]  = (unsigned short)(ok ? bucket : kInvalidKey);
-          if (ok) {
-            stage_cw[slot] = make_float2(fc, w);
-            atomicAdd(&my_hw32[bucket >> 1], 1u << ((bucket & 1u) * 16u));
+          basev = __shfl_sync(0xffffffffu, basev, lead);
+          const unsigned rk = (unsigned)(basev + __popc(m[j] & ((1u << lane) - 1u)));
+          if (((s4 + j) & 1) == 0) {
+            rank_pack[(s4 + j) >> 1] = rk;
+          } else {
+            rank_pack[(s4 + j) >> 1] |= rk << 16;
           }
+          __syncwarp();
         }
       }
       __syncthreads();
-      // ---- scan: bucket totals (padded to even) -> start[], per-warp cursors, and
-      // the prefix of the pair-phase cost model (entries + kSegCost per non-empty
-      // bucket) that the warp rows split evenly between them
+      // ---- scan: bucket totals (padded to even) -> per-warp cursors and the list
+      // of non-empty buckets ("segments": bucket id + start in the sorted array).
+      // Entries and segments are scanned together, packed 16 + 16 bits.
       {
-        int sum = 0, csum = 0;
+        int sum = 0;
         for (int i = 0; i < bpt; ++i) {
           const int b = tid * bpt + i;
           if (b < nb) {
@@ -313,131 +445,148 @@ namespace rgc {
               tot += hw16[wq * nbp + b];
             }
             const int pc = (tot + 1) & ~1;
-            sum += pc;
-            csum += pc + (pc ? kSegCost : 0);
+            sum += pc + (pc ? 0x10000 : 0);
           }
         }
-        int incl = sum, cincl = csum;
+        int incl = sum;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
-          const int t  = __shfl_up_sync(0xffffffffu, incl, off);
-          const int tc = __shfl_up_sync(0xffffffffu, cincl, off);
+          const int t = __shfl_up_sync(0xffffffffu, incl, off);
           if (lane >= off) {
             incl += t;
-            cincl += tc;
           }
         }
         if (lane == 31) {
-          scan_tmp[warp]           = incl;
-          scan_tmp[kPWarps + warp] = cincl;
+          scan_tmp[warp] = incl;
         }
         __syncthreads();
-        int warp_base = 0, total = 0, cwarp_base = 0, ctotal = 0;
+        int warp_base = 0, total = 0;
 #pragma unroll
         for (int wq = 0; wq < kPWarps; ++wq) {
-          const int c  = scan_tmp[wq];
-          const int cc = scan_tmp[kPWarps + wq];
+          const int c = scan_tmp[wq];
           warp_base += wq < warp ? c : 0;
-          cwarp_base += wq < warp ? cc : 0;
           total += c;
-          ctotal += cc;
         }
-        int off  = warp_base + incl - sum;
-        int coff = cwarp_base + cincl - csum;
+        int packed = warp_base + incl - sum;
         for (int i = 0; i < bpt; ++i) {
           const int b = tid * bpt + i;
           if (b < nb) {
-            start[b]  = off;
-            cstart[b] = coff;
-            int run   = off;
+            const int off = packed & 0xffff, k = packed >> 16;
+            int       run = off;
 #pragma unroll
             for (int wq = 0; wq < kPWarps; ++wq) {
               const int c        = hw16[wq * nbp + b];
               hw16[wq * nbp + b] = (unsigned short)run;
               run += c;
             }
-            if ((run - off) & 1) {
-              sorted[run] = make_float2(0.0f, 0.0f); // zero-weight pad
-              ++run;
+            if (run != off) {
+              if ((run - off) & 1) {
+                sorted[run] = make_float2(0.0f, 0.0f); // zero-weight pad
+                ++run;
+              }
+              seg_start[k] = off;
+              seg_b[k]     = b;
+              seg_s0[k]    = 0.0f;
+              seg_s1[k]    = 0.0f;
+              packed += (run - off) + 0x10000;
             }
-            coff += (run - off) + (run != off ? kSegCost : 0);
-            off = run;
           }
         }
         if (tid == 0) {
-          start[nb]  = total;
-          cstart[nb] = ctotal;
+          const int nseg  = total >> 16;
+          seg_start[nseg] = total & 0xffff;
+          seg_b[nseg]     = 0;
+          scan_tmp[kPWarps] = nseg;
         }
       }
       __syncthreads();
-      // ---- pass 2: stable ranking inside the warp, scatter to bucket order
+      // ---- pass B: scatter to bucket order (cursor base of (warp, bucket) + rank)
       {
-        unsigned short* cur = hw16 + warp * nbp;
-#pragma unroll 1
+        const unsigned short* basep = hw16 + warp * nbp;
+#pragma unroll
         for (int step = 0; step < kPSteps; ++step) {
-          const int      slot  = step * kPThreads + tid;
-          const unsigned key   = stage_k[slot];
-          const bool     valid = key != kInvalidKey;
-          const unsigned m     = __match_any_sync(0xffffffffu, key);
-          const int      lead  = __ffs(m) - 1;
-          const int      rank  = __popc(m & ((1u << lane) - 1u));
-          int            basev = 0;
-          if (valid && lane == lead) {
-            basev    = cur[key];
-            cur[key] = (unsigned short)(basev + __popc(m));
+          const int      idx = warp * (kPTile / kPWarps) + step * 32 + lane;
+          const unsigned key = stage_k[idx];
+          if (key != kInvalidKey) {
+            const unsigned rk = (rank_pack[step >> 1] >> ((step & 1) * 16)) & 0xffffu;
+            sorted[(unsigned)basep[key] + rk] = stage_cw[idx];
           }
-          basev = __shfl_sync(0xffffffffu, basev, lead);
-          if (valid) {
-            sorted[basev + rank] = stage_cw[slot];
-          }
-          __syncwarp();
         }
       }
       __syncthreads();
-      // ---- pair phase
+      // staging buffers are free again: fetch the next tile underneath the pair loop
+      if (tid == 0 && tile + gridDim.x < ntiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_tile_copy(tile + gridDim.x);
+      }
+      // ---- pair phase: the segment list is split between the warp rows by the cost
+      // model  entries + seg_cost * segments;  a row boundary inside a bucket splits
+      // that bucket's segment
       {
-        const int total  = start[nb];
-        const int ctotal = cstart[nb];
-        // position in the sorted array at which the cost prefix reaches `target`
-        // (even; a row boundary inside a bucket splits that bucket's segment)
-        auto pos_of_cost = [&](int target, int& bucket_out) -> int {
-          int l = 0, h = nb - 1;
-          while (l < h) {
+        const int nseg  = scan_tmp[kPWarps];
+        const int total = seg_start[nseg];
+        const int segc  = P.seg_cost;
+        auto pos_of_cost = [&](int target, int& k_out) -> int {
+          int l = 0, h = max(nseg - 1, 0);
+          while (l < h) { // largest k with cost_before(k) <= target
             const int mid = (l + h + 1) >> 1;
-            if (cstart[mid] <= target) {
+            if (seg_start[mid] + segc * mid <= target) {
               l = mid;
             } else {
               h = mid - 1;
             }
           }
-          bucket_out      = l;
-          const int s0    = start[l];
-          const int within = max(0, target - cstart[l] - kSegCost) & ~1;
-          return min(start[l + 1], s0 + within);
+          k_out           = l;
+          const int s0    = seg_start[l];
+          const int within = max(0, target - (s0 + segc * l) - segc) & ~1;
+          return min(seg_start[l + 1], s0 + within);
         };
-        int b = 0, bdummy = 0;
-        const int lo = row == 0 ? 0 : pos_of_cost((int)(((long long)ctotal * row) / rows), b);
-        const int hi = row == rows - 1 ? total
-                                       : pos_of_cost((int)(((long long)ctotal * (row + 1)) / rows), bdummy);
+        const int ctotal = total + segc * nseg;
+        int       k = 0, kdummy = 0;
+        const int lo = row == 0 ? 0 : pos_of_cost((int)(((long long)ctotal * row) / rows), k);
+        const int hi = row == rows - 1
+                         ? total
+                         : pos_of_cost((int)(((long long)ctotal * (row + 1)) / rows), kdummy);
         if (lo < hi) {
-          int pos    = lo;
-          int nedges = 0;
+          if (seg_start[k + 1] <= lo) {
+            ++k;
+          }
           const float4* sorted4 = reinterpret_cast<const float4*>(sorted);
-          while (pos < hi) {
-            while (start[b + 1] <= pos) {
-              ++b;
+          int           nedges  = 0;
+          // coefficients of the current segment; those of the next one are fetched
+          // before the pair loop runs so their latency hides underneath it
+          int   b_cur = seg_b[k];
+          int   s_beg = seg_start[k], s_end = seg_start[k + 1];
+          float fap[GPW], sgn[GPW], ds[GPW];
+#pragma unroll
+          for (int g = 0; g < GPW; ++g) {
+            const float4 dh = coef[max(aoff[g] + b_cur, 0)];
+            ds[g]  = dh.x;
+            sgn[g] = dh.z;
+            fap[g] = (fa0[g] - dh.y) * dh.z;
+          }
+          for (;;) {
+            const int  pos  = max(s_beg, lo);
+            const int  end  = min(s_end, hi);
+            const bool full = (pos == s_beg) && (end == s_end);
+            const bool more = s_end < hi;
+            // next segment (reads one past the list's end are harmless: k + 2 <= nseg + 1
+            // is guarded by `more`)
+            int    b_nxt = 0, n_beg = 0, n_end = 0;
+            float4 dhn[GPW];
+            if (more) {
+              b_nxt = seg_b[k + 1];
+              n_beg = s_end;
+              n_end = seg_start[k + 2];
+#pragma unroll
+              for (int g = 0; g < GPW; ++g) {
+                dhn[g] = coef[max(aoff[g] + b_nxt, 0)];
+              }
             }
-            const int  bend = start[b + 1];
-            const int  end  = min(hi, bend);
-            const bool full = (pos == start[b]) && (end == bend);
-            float      fap[GPW], sgn[GPW], ds[GPW], s2[GPW];
+            float s2[GPW];
 #pragma unroll
             for (int g = 0; g < GPW; ++g) {
-              const float4 dh = coef[max(aoff[g] + b, 0)];
-              ds[g]  = dh.x;
-              sgn[g] = dh.z;
-              fap[g] = (fa0[g] - dh.y) * dh.z;
-              s2[g]  = 0.0f;
+              s2[g] = 0.0f;
             }
             // Two particles per broadcast LDS.128; the loads of the next two float4
             // are in flight while the current two are consumed (ping-pong registers,
@@ -481,26 +630,34 @@ namespace rgc {
             for (int g = 0; g < GPW; ++g) {
               acc[g] = fmaf(ds[g], s2[g], acc[g]);
             }
-            if (col == 0) {
-              // spare lanes 30 / 31 of the last group carry S0 / S1 of this segment
-              const float seg_s0 = __shfl_sync(0xffffffffu, s2[GPW - 1], 30);
-              const float seg_s1 = __shfl_sync(0xffffffffu, s2[GPW - 1], 31);
-              if (lane == 0) {
-                if (full) {
-                  s0tot[b] += (double)seg_s0;
-                  s1tot[b] += (double)seg_s1;
-                } else {
-                  PairEdge& ed = edge[row * 2 + nedges];
-                  ed.b  = b;
-                  ed.s0 = seg_s0;
-                  ed.s1 = seg_s1;
-                }
-              }
-              if (!full) {
-                ++nedges;
+            if (col == 0 && lane >= 30) {
+              // spare lanes 30 / 31 of the last group carry S0 / S1 of this segment:
+              // plain stores, folded into the fp64 bucket moments after the barrier
+              const float v = s2[GPW - 1];
+              if (full) {
+                (lane == 30 ? seg_s0 : seg_s1)[k] = v;
+              } else {
+                PairEdge& ed = edge[row * 2 + nedges];
+                ed.b         = b_cur;
+                (lane == 30 ? ed.s0 : ed.s1) = v;
               }
             }
-            pos = end;
+            if (!full) {
+              ++nedges;
+            }
+            if (!more) {
+              break;
+            }
+            ++k;
+            b_cur = b_nxt;
+            s_beg = n_beg;
+            s_end = n_end;
+#pragma unroll
+            for (int g = 0; g < GPW; ++g) {
+              ds[g]  = dhn[g].x;
+              sgn[g] = dhn[g].z;
+              fap[g] = (fa0[g] - dhn[g].y) * dhn[g].z;
+            }
           }
         }
 #pragma unroll
@@ -510,16 +667,27 @@ namespace rgc {
         }
       }
       __syncthreads();
-      // segments cut by a row boundary: fold their moments in row order
-      if (tid == 0) {
-        for (int i = 0; i < rows * 2; ++i) {
-          const PairEdge ed = edge[i];
-          if (ed.b >= 0) {
-            s0tot[ed.b] += (double)ed.s0;
-            s1tot[ed.b] += (double)ed.s1;
-            edge[i].b = -1;
+      // ---- fold the segments' moments into the fp64 bucket moments: one thread per
+      // segment; the (at most two per row) pieces of segments cut by a row boundary
+      // are added by the same thread, in row order
+      {
+        const int nseg = scan_tmp[kPWarps];
+        for (int kk = tid; kk < nseg; kk += kPThreads) {
+          const int b  = seg_b[kk];
+          double    a0 = (double)seg_s0[kk], a1 = (double)seg_s1[kk];
+          for (int i = 0; i < rows * 2; ++i) {
+            if (edge[i].b == b) {
+              a0 += (double)edge[i].s0;
+              a1 += (double)edge[i].s1;
+            }
           }
+          s0tot[b] += a0;
+          s1tot[b] += a1;
         }
+      }
+      __syncthreads();
+      if (tid < kPWarps * 2) {
+        edge[tid].b = -1;
       }
     }
 
@@ -744,9 +912,14 @@ namespace rgc {
     if (smem > 227 * 1024) {
       return fail(RGC_ERR_INVALID, "internal: pair kernel needs %zu B of shared memory", smem);
     }
-    const std::size_t ntiles = (n + kPTile - 1) / kPTile;
+    // particles are processed in chunks so the staged (fc, w, key) stay bounded
+    // (10 B per particle); chunk results are summed on the host in chunk order
+    const std::size_t chunk_max = std::size_t(1) << 27;
+    const std::size_t nchunk0   = std::min(n, chunk_max);
+    const std::size_t ntiles0   = (nchunk0 + kPTile - 1) / kPTile;
+    const std::size_t npad0     = ntiles0 * kPTile;
     const int nctas = (int)std::min<std::size_t>((std::size_t)c.sm_count * per_sm,
-                                                 std::max<std::size_t>(ntiles, 1));
+                                                 std::max<std::size_t>(ntiles0, 1));
     auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
     const std::size_t off_si   = 0;
     const std::size_t off_sf   = align(off_si + pp.nslots * sizeof(int2));
@@ -756,7 +929,9 @@ namespace rgc {
     const std::size_t off_out  = align(off_msum + 2 * pp.nb * sizeof(double));
     const std::size_t off_part = align(off_out + pp.nslots * sizeof(double));
     const std::size_t off_mom  = align(off_part + (std::size_t)nctas * pp.nslots * sizeof(double));
-    const std::size_t total    = off_mom + (std::size_t)nctas * 2 * pp.nb * sizeof(double);
+    const std::size_t off_cw   = align(off_mom + (std::size_t)nctas * 2 * pp.nb * sizeof(double));
+    const std::size_t off_keys = align(off_cw + npad0 * sizeof(float2));
+    const std::size_t total    = off_keys + npad0 * sizeof(unsigned short);
     void*             scratch  = nullptr;
     RGC_TRY(ensure_scratch(total, &scratch));
     char* sb = static_cast<char*>(scratch);
@@ -769,12 +944,6 @@ namespace rgc {
     RGC_CUDA(cudaMemcpyAsync(sb + off_vs, pp.coef_vs.data(), pp.n_pad * sizeof(double2),
                              cudaMemcpyHostToDevice, c.stream));
     PairParams P {};
-    for (int d = 0; d < 3; ++d) {
-      P.u[d] = prtls->col[RGC_Q_U][d];
-      P.e[d] = prtls->col[RGC_Q_E][d];
-      P.b[d] = prtls->col[RGC_Q_B][d];
-    }
-    P.nprtl    = n;
     P.slot_i   = reinterpret_cast<const int2*>(sb + off_si);
     P.slot_f   = reinterpret_cast<const float2*>(sb + off_sf);
     P.coef_dh  = reinterpret_cast<const float4*>(sb + off_dh);
@@ -783,6 +952,7 @@ namespace rgc {
     P.nbp      = pp.nbp;
     P.ncols    = pp.ncols;
     P.kmin     = pp.kmin;
+    P.kmin_d   = (double)pp.kmin;
     P.inv_B0           = 1.0 / (double)B0;
     P.e_scale          = (double)e_at / (double)(g_syn * g_syn);
     P.cells_per_octave = 0.30102999566398119521 / tp.dL;
@@ -790,36 +960,73 @@ namespace rgc {
     P.inv_dL   = 1.0 / tp.dL;
     P.c_lo     = pp.c_lo;
     P.c_hi     = pp.c_hi;
+    P.cw       = reinterpret_cast<float2*>(sb + off_cw);
+    P.keys     = reinterpret_cast<unsigned short*>(sb + off_keys);
     P.partials = reinterpret_cast<double*>(sb + off_part);
     P.moments  = reinterpret_cast<double*>(sb + off_mom);
     P.nslots   = pp.nslots;
+    {
+      const char* sc = std::getenv("RGC_PAIR_SEG_COST"); // tuning knob
+      P.seg_cost     = sc ? std::max(0, std::atoi(sc)) : kSegCostDefault;
+    }
     P.o_coef = (int)L.coef; P.o_s0tot = (int)L.s0tot; P.o_s1tot = (int)L.s1tot;
     P.o_start = (int)L.start; P.o_cstart = (int)L.cstart; P.o_hw = (int)L.hw;
     P.o_stage_cw = (int)L.stage_cw; P.o_stage_k = (int)L.stage_k; P.o_sorted = (int)L.sorted;
-    P.o_edge = (int)L.edge; P.o_scan = (int)L.scan;
-    RGC_CUDA(cudaEventRecord(c.ev[2], c.stream));
-    RGC_TRY(launch_pair(pp.gpw, dim3(nctas), smem, c.stream, P));
-    RGC_CUDA(cudaGetLastError());
-    RGC_CUDA(cudaEventRecord(c.ev[3], c.stream));
+    P.o_edge = (int)L.edge; P.o_scan = (int)L.scan; P.o_mbar = (int)L.mbar;
+    P.o_seg_s0 = (int)L.seg_s0; P.o_seg_s1 = (int)L.seg_s1;
     double* d_msum = reinterpret_cast<double*>(sb + off_msum);
     double* d_out  = reinterpret_cast<double*>(sb + off_out);
-    pair_moments_kernel<<<(2 * pp.nb + 127) / 128, 128, 0, c.stream>>>(P.moments, nctas, 2 * pp.nb,
-                                                                       d_msum);
-    RGC_CUDA(cudaGetLastError());
-    pair_final_kernel<<<(pp.nslots + 63) / 64, 64, 0, c.stream>>>(
-      P.partials, nctas, pp.nslots, P.slot_i, P.slot_f,
-      reinterpret_cast<const double2*>(sb + off_vs), d_msum, pp.nb, d_out);
-    RGC_CUDA(cudaGetLastError());
-    count_launch(3);
-    std::vector<double> out_host(pp.nslots);
-    RGC_CUDA(cudaMemcpyAsync(out_host.data(), d_out, pp.nslots * sizeof(double),
-                             cudaMemcpyDeviceToHost, c.stream));
-    RGC_CUDA(cudaStreamSynchronize(c.stream));
-    float ms = 0.f;
-    RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]));
-    if (main_ms) {
-      *main_ms += ms;
+    std::vector<double> out_host(pp.nslots), out_sum(pp.nslots, 0.0);
+    float               pro_ms = 0.f;
+    const char*         pm       = std::getenv("RGC_PROLOGUE_MINB"); // tuning knob
+    const int           pro_minb = pm ? std::atoi(pm) : 3;
+    for (std::size_t off = 0; off < n; off += chunk_max) {
+      const std::size_t cnt = std::min(chunk_max, n - off);
+      for (int d = 0; d < 3; ++d) {
+        P.u[d] = prtls->col[RGC_Q_U][d] + off;
+        P.e[d] = prtls->col[RGC_Q_E][d] + off;
+        P.b[d] = prtls->col[RGC_Q_B][d] + off;
+      }
+      P.nprtl = cnt;
+      P.npad  = ((cnt + kPTile - 1) / kPTile) * kPTile;
+      const int grid1 = (int)std::min<std::size_t>((std::size_t)c.sm_count * 8,
+                                                   (P.npad / 4 + 255) / 256);
+      const int grid2 = (int)std::min<std::size_t>((std::size_t)nctas, P.npad / kPTile);
+      RGC_CUDA(cudaEventRecord(c.ev[2], c.stream));
+      if (pro_minb == 4) {
+        sync_prologue_kernel<4><<<grid1, 256, 0, c.stream>>>(P);
+      } else {
+        sync_prologue_kernel<3><<<grid1, 256, 0, c.stream>>>(P);
+      }
+      RGC_CUDA(cudaGetLastError());
+      RGC_CUDA(cudaEventRecord(c.ev[3], c.stream));
+      RGC_TRY(launch_pair(pp.gpw, dim3(grid2), smem, c.stream, P));
+      RGC_CUDA(cudaGetLastError());
+      RGC_CUDA(cudaEventRecord(c.ev[4], c.stream));
+      pair_moments_kernel<<<(2 * pp.nb + 127) / 128, 128, 0, c.stream>>>(P.moments, grid2,
+                                                                         2 * pp.nb, d_msum);
+      RGC_CUDA(cudaGetLastError());
+      pair_final_kernel<<<(pp.nslots + 63) / 64, 64, 0, c.stream>>>(
+        P.partials, grid2, pp.nslots, P.slot_i, P.slot_f,
+        reinterpret_cast<const double2*>(sb + off_vs), d_msum, pp.nb, d_out);
+      RGC_CUDA(cudaGetLastError());
+      count_launch(4);
+      RGC_CUDA(cudaMemcpyAsync(out_host.data(), d_out, pp.nslots * sizeof(double),
+                               cudaMemcpyDeviceToHost, c.stream));
+      RGC_CUDA(cudaStreamSynchronize(c.stream));
+      float ms = 0.f;
+      RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[3], c.ev[4]));
+      if (main_ms) {
+        *main_ms += ms;
+      }
+      RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]));
+      pro_ms += ms;
+      for (int s2 = 0; s2 < pp.nslots; ++s2) {
+        out_sum[s2] += out_host[s2];
+      }
     }
+    c.last_ms[2] = pro_ms;
+    out_host.swap(out_sum);
     // bins[] is in chunk order; slots were filled in the same order
     acc.assign(bins.size(), 0.0);
     const int cap = pp.gpw * 32 - 2;
