@@ -221,12 +221,57 @@ int rgc_last_kernel_times(float* ms, int n);
  * device's nominal SM clock. */
 int rgc_measure_peak(int kind, double* value, double* sm_clock_mhz);
 
+/* ------------------------------------------------------------ HDF5 arrays */
+
+/* A self-contained HDF5 layer stands in for HighFive v2.10.1 + libhdf5 (the
+ * reference's un-vendored dependency, cmake/dependencies.cmake:15-18).  Reads files
+ * written by libhdf5 (superblock v0-v3, old- and new-style compact groups, IEEE
+ * float / integer types of either byte order, contiguous / compact / chunked
+ * layouts with deflate, shuffle and fletcher32); writes superblock-v0 files with
+ * contiguous datasets, as libhdf5 does with default property lists.  The
+ * rgc_h5_open..rgc_h5_write group is pure host code and works without a GPU. */
+typedef struct rgc_h5 rgc_h5_t;
+#define RGC_H5_READONLY  0 /* HighFive::File::ReadOnly */
+#define RGC_H5_READWRITE 1 /* ReadWrite | Create: append datasets, create if missing */
+#define RGC_H5_TRUNCATE  2 /* start a new file */
+#define RGC_H5_CLASS_INTEGER 0
+#define RGC_H5_CLASS_FLOAT   1
+#define RGC_H5_LAYOUT_COMPACT    0
+#define RGC_H5_LAYOUT_CONTIGUOUS 1
+#define RGC_H5_LAYOUT_CHUNKED    2
+/* HighFive::File{filename, mode} — src/plugins/tristan-v2.cpp:117, src/io/h5.cpp:21,54 */
+int rgc_h5_open(const char* filename, int mode, rgc_h5_t** out);
+int rgc_h5_close(rgc_h5_t* f);
+/* newline-separated link names of a group ("/" or NULL = root), NUL-terminated;
+ * *needed receives the buffer size the full list takes */
+int rgc_h5_list(rgc_h5_t* f, const char* group, char* names, size_t cap, size_t* needed);
+/* file.getDataSet(name).getDimensions() — tristan-v2.cpp:58-59,125; h5.cpp:22-23 */
+int rgc_h5_dataset_info(rgc_h5_t* f, const char* name, int* rank, uint64_t* dims,
+                        int max_rank, int* type_class, int* elem_size, int* layout);
+/* dataset.select({start},{count},{stride}).read<T>(host) — tristan-v2.cpp:72,
+ * h5.cpp:40; dtype = RGC_I32/F32/F64 of the destination (source types convert) */
+int rgc_h5_read(rgc_h5_t* f, const char* name, size_t start, size_t count, size_t stride,
+                int dtype, void* host);
+/* file.createDataSet<T>(name, DataSpace({n})) — h5.cpp:59-60 (contiguous, zero-filled) */
+int rgc_h5_create_dataset(rgc_h5_t* f, const char* name, int dtype, size_t n);
+/* write_raw of elements [start, start+count) — h5.cpp:61 */
+int rgc_h5_write(rgc_h5_t* f, const char* name, size_t start, size_t count, int dtype,
+                 const void* host);
+/* io::h5::Read1DArray<T> — src/io/h5.cpp:16-48: selection {0},{size or extent},{stride}
+ * streamed disk -> pinned lanes -> device.  Same checks and messages as the reference. */
+int rgc_h5_read_array(const char* filename, const char* dsetname, int dtype, size_t size,
+                      size_t stride, rgc_buf_t** out);
+/* io::h5::Write1DArray<T> — src/io/h5.cpp:50-68: opens ReadWrite|Create, creates the
+ * dataset (fails if it exists) and writes the array */
+int rgc_h5_write_array(const char* filename, const char* dsetname, const rgc_buf_t* array);
+
 /* ------------------------------------------------------ Tristan-v2 plugin */
 
 /* TristanV2<D>::readParticles — src/plugins/tristan-v2.cpp:95-188.  Opens
  * <path>/output/prtl/prtl.tot.<step:05d> (HDF5), reads x_/y_/z_ (first dim, unless
  * ignore_coords), u_/v_/w_, ex_/ey_/ez_, bx_/by_/bz_<sp> as float32 hyperslabs
- * [start, start+count*stride) and streams them disk -> pinned ring -> device.
+ * [start, start+count*stride) and streams them disk -> pinned lanes -> device
+ * (all columns concurrently, several I/O threads; $RGC_IO_THREADS overrides).
  * *ntotal receives the dataset length, *nread the particles stored.  Validation
  * (stride == 0, stride != 1 with size != 0, start + size >= ntotal) follows
  * tristan-v2.cpp:102-107,126-128 and returns RGC_ERR_INVALID with the reference's
@@ -236,8 +281,10 @@ int rgc_tristan_read_particles(const char* path, size_t step, unsigned sp, size_
                                rgc_particles_t** out, size_t* ntotal, size_t* nread);
 /* writes a synthetic Tristan-v2 particle file (test / bench fixture generator):
  * datasets named as above for species sp, n floats each, contiguous float32.
- * columns[k] may be NULL (dataset of zeros).  append != 0 adds a species to an
- * existing file written by this function. */
+ * columns = x,y,z (only when with_coords), u,v,w, ex,ey,ez, bx,by,bz; columns[k]
+ * may be NULL (sparse dataset of zeros; x_/y_/z_ are always created because the
+ * reader sizes the species from x_<sp>).  append != 0 adds a species to an
+ * existing file.  Host-only (no GPU needed). */
 int rgc_tristan_write_species(const char* path, size_t step, unsigned sp, size_t n,
                               int with_coords, const float* const* columns, int append);
 

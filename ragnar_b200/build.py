@@ -81,7 +81,7 @@ def build(force: bool = False, verbose: bool = False) -> dict:
     (OBJ / "ptxas.log").write_text("\n".join(f"== {k}\n{v}" for k, v in logs.items()))
     if force or jobs or not LIB.exists():
         _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs), "-cudart", "static",
-              "-Xlinker", "--exclude-libs,ALL", "-ldl", "-lpthread"], verbose)
+              "-Xlinker", "--exclude-libs,ALL", "-ldl", "-lpthread", "-lz"], verbose)
     # pybind11 module
     import pybind11
 

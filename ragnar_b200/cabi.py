@@ -76,6 +76,17 @@ SIGNATURES = {
     "rgc_last_kernel_ms": (C.c_int, [_f32p]),
     "rgc_last_kernel_times": (C.c_int, [_f32p, C.c_int]),
     "rgc_measure_peak": (C.c_int, [C.c_int, _f64p, _f64p]),
+    "rgc_h5_open": (C.c_int, [C.c_char_p, C.c_int, _vpp]),
+    "rgc_h5_close": (C.c_int, [_vp]),
+    "rgc_h5_list": (C.c_int, [_vp, C.c_char_p, C.c_char_p, _sz, C.POINTER(_sz)]),
+    "rgc_h5_dataset_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int), _u64p, C.c_int,
+                                      C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int)]),
+    "rgc_h5_read": (C.c_int, [_vp, C.c_char_p, _sz, _sz, _sz, C.c_int, _vp]),
+    "rgc_h5_create_dataset": (C.c_int, [_vp, C.c_char_p, C.c_int, _sz]),
+    "rgc_h5_write": (C.c_int, [_vp, C.c_char_p, _sz, _sz, C.c_int, _vp]),
+    "rgc_h5_read_array": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, _sz, _sz, _vpp]),
+    "rgc_h5_write_array": (C.c_int, [C.c_char_p, C.c_char_p, _vp]),
     "rgc_tristan_read_particles": (C.c_int, [C.c_char_p, _sz, C.c_uint, _sz, _sz, _sz, C.c_int,
                                              C.c_int, _vpp, C.POINTER(_sz), C.POINTER(_sz)]),
     "rgc_tristan_write_species": (C.c_int, [C.c_char_p, _sz, C.c_uint, _sz, C.c_int,
@@ -387,3 +398,70 @@ def tristan_read_particles(path: str, step: int, sp: int, start=0, size=0, strid
                                            C.byref(ntotal), C.byref(nread)))
     p.n = nread.value
     return p, ntotal.value
+
+
+# ------------------------------------------------------------------ HDF5 (host side)
+_NP_OF = {I32: np.int32, F32: np.float32, F64: np.float64}
+_DTYPE_OF = {np.dtype(np.int32): I32, np.dtype(np.float32): F32,
+             np.dtype(np.float64): F64}
+
+
+class H5File:
+    """Host-side view of the library's HDF5 layer (rgc_h5_*): no GPU required.
+    mode: "r" (ReadOnly), "a" (ReadWrite | Create), "w" (truncate)."""
+
+    def __init__(self, filename: str, mode: str = "r"):
+        self.h = _vp()
+        check(lib().rgc_h5_open(str(filename).encode(), {"r": 0, "a": 1, "w": 2}[mode],
+                                C.byref(self.h)))
+
+    def close(self) -> None:
+        if self.h:
+            h, self.h = self.h, _vp()
+            check(lib().rgc_h5_close(h))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def list(self, group: str = "/"):
+        need = _sz()
+        check(lib().rgc_h5_list(self.h, group.encode(), None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        check(lib().rgc_h5_list(self.h, group.encode(), buf, need.value, None))
+        return [s for s in buf.value.decode().split("\n") if s]
+
+    def info(self, name: str) -> dict:
+        rank, cls, es, layout = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        dims = (C.c_uint64 * 8)()
+        check(lib().rgc_h5_dataset_info(self.h, name.encode(), C.byref(rank), dims, 8,
+                                        C.byref(cls), C.byref(es), C.byref(layout)))
+        return {"dims": [int(dims[k]) for k in range(rank.value)], "class": cls.value,
+                "elem_size": es.value, "layout": layout.value}
+
+    def read(self, name: str, start: int = 0, count: int | None = None, stride: int = 1,
+             dtype=np.float32) -> np.ndarray:
+        if count is None:
+            dims = self.info(name)["dims"]
+            total = int(np.prod(dims)) if dims else 1
+            count = (total - start + stride - 1) // stride if total > start else 0
+        out = np.empty(count, dtype)
+        check(lib().rgc_h5_read(self.h, name.encode(), start, count, stride,
+                                _DTYPE_OF[np.dtype(dtype)], out.ctypes.data_as(_vp)))
+        return out
+
+    def create_dataset(self, name: str, dtype, n: int) -> None:
+        check(lib().rgc_h5_create_dataset(self.h, name.encode(), _DTYPE_OF[np.dtype(dtype)], n))
+
+    def write(self, name: str, data: np.ndarray, start: int = 0) -> None:
+        data = np.ascontiguousarray(data)
+        check(lib().rgc_h5_write(self.h, name.encode(), start, data.size,
+                                 _DTYPE_OF[data.dtype], data.ctypes.data_as(_vp)))

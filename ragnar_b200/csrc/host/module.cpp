@@ -38,6 +38,7 @@ PYBIND11_MODULE(ragnar, m) {
   rgb::define_tabulated_functions(m);
   rgb::define_arrays_and_bins(m);
   rgb::define_particles(m);
+  rgb::define_h5(m);
   rgb::define_tristan(m);
   rgb::define_generators(m);
   rgb::define_synchrotron(m);

@@ -100,8 +100,8 @@ namespace rgb {
           "bins_e_syn"_a, "g_syn"_a, "e_syn_at_g_syn"_a, doc::SynchrotronSpectrumFromDist);
   }
 
-  // exported with the reference's signatures and
-  // docstrings, not implemented yet (there is no CPU path to route them to)
+  // exported with the reference's signature and docstring,
+  // not implemented yet (there is no CPU path to route it to)
   void define_not_yet(py::module& m) {
     m.def(
       "ICSpectrum",
@@ -111,26 +111,6 @@ namespace rgb {
         throw py::error_already_set();
       },
       "dist_prtls"_a, "dist_soft_photons"_a, "bins_e_ic"_a, doc::ICSpectrum);
-    for (const char* suffix : { "i", "f", "d" }) {
-      m.def(
-        (std::string("H5read1DArray_") + suffix).c_str(),
-        [](const std::string&, const std::string&, std::size_t, std::size_t) {
-          PyErr_SetString(PyExc_NotImplementedError,
-                          "generic HDF5 array I/O is outside the B200 hot path of this build "
-                          "(SURVEY.md 8f-f2)");
-          throw py::error_already_set();
-        },
-        "filename"_a, "dsetname"_a, "size"_a = 0, "stride"_a = 1, doc::H5read1DArray);
-      m.def(
-        (std::string("H5write1DArray_") + suffix).c_str(),
-        [](const std::string&, const std::string&, const py::object&) {
-          PyErr_SetString(PyExc_NotImplementedError,
-                          "generic HDF5 array I/O is outside the B200 hot path of this build "
-                          "(SURVEY.md 8f-f2)");
-          throw py::error_already_set();
-        },
-        "filename"_a, "dsetname"_a, "array"_a, doc::H5write1DArray);
-    }
   }
 
 } // namespace rgb

@@ -90,6 +90,89 @@ namespace rgb {
       .doc() = doc::Tristan_class;
   }
 
+  // ------------------------------------------------------------------ io::h5
+  // reference src/io/h5.cpp:16-48
+  template <class T>
+  static Array1D<T> H5Read1DArray(const std::string& filename, const std::string& dsetname,
+                                  std::size_t size, std::size_t stride) {
+    { // the reference validates before it prints (h5.cpp:21-35)
+      rgc_h5_t* f = nullptr;
+      check(rgc_h5_open(filename.c_str(), RGC_H5_READONLY, &f));
+      int       rank = 0;
+      uint64_t  dims[8] {};
+      const int rc = rgc_h5_dataset_info(f, dsetname.c_str(), &rank, dims, 8, nullptr, nullptr,
+                                         nullptr);
+      const std::string msg = rc == RGC_OK ? "" : rgc_last_error();
+      rgc_h5_close(f);
+      if (rc != RGC_OK) {
+        throw std::runtime_error(msg);
+      }
+      if (rank != 1) {
+        throw std::runtime_error("Dataset is not 1D");
+      }
+      if (stride == 0) {
+        throw std::runtime_error("Stride must be greater than 0");
+      } else if (size != 0 and dims[0] / stride > size) {
+        throw std::runtime_error("Number of read quantity exceeds allocated space");
+      }
+    }
+    py::print("Reading", dsetname, "from", filename, "...", "end"_a = "", "flush"_a = true);
+    rgc_buf_t* buf = nullptr;
+    if (rgc_h5_read_array(filename.c_str(), dsetname.c_str(), dtype_of<T>(), size, stride, &buf) !=
+        RGC_OK) {
+      const std::string what = rgc_last_error();
+      py::print("Error reading", dsetname, "from", filename, ":", what);
+      throw std::runtime_error(what);
+    }
+    py::print(": OK", "flush"_a = true);
+    return Array1D<T>::adopt(buf);
+  }
+
+  // reference src/io/h5.cpp:50-68
+  template <class T>
+  static void H5Write1DArray(const std::string& filename, const std::string& dsetname,
+                             const Array1D<T>& array) {
+    py::print("Writing", dsetname, "to", filename, "...", "end"_a = "", "flush"_a = true);
+    int rc = RGC_OK;
+    if (array.handle() != nullptr) {
+      rc = rgc_h5_write_array(filename.c_str(), dsetname.c_str(), array.handle());
+    } else { // an empty Array1D: a dataset of extent 0
+      rgc_h5_t* f = nullptr;
+      rc          = rgc_h5_open(filename.c_str(), RGC_H5_READWRITE, &f);
+      if (rc == RGC_OK) {
+        rc = rgc_h5_create_dataset(f, dsetname.c_str(), dtype_of<T>(), 0);
+        const std::string keep = rc == RGC_OK ? "" : rgc_last_error();
+        const int         rc2  = rgc_h5_close(f);
+        if (rc != RGC_OK) {
+          py::print("Error writing", dsetname, "to", filename, ":", keep);
+          throw std::runtime_error(keep);
+        }
+        rc = rc2;
+      }
+    }
+    if (rc != RGC_OK) {
+      const std::string what = rgc_last_error();
+      py::print("Error writing", dsetname, "to", filename, ":", what);
+      throw std::runtime_error(what);
+    }
+    py::print(": OK", "flush"_a = true);
+  }
+
+  template <class T>
+  static void define_h5_t(py::module& m, const char* suffix) {
+    m.def((std::string("H5read1DArray_") + suffix).c_str(), &H5Read1DArray<T>, "filename"_a,
+          "dsetname"_a, "size"_a = 0, "stride"_a = 1, doc::H5read1DArray);
+    m.def((std::string("H5write1DArray_") + suffix).c_str(), &H5Write1DArray<T>, "filename"_a,
+          "dsetname"_a, "array"_a, doc::H5write1DArray);
+  }
+
+  // suffixes are typeid(T).name() in the reference (h5.cpp:72,96): i, f, d
+  void define_h5(py::module& m) {
+    define_h5_t<int>(m, "i");
+    define_h5_t<real_t>(m, "f");
+    define_h5_t<double>(m, "d");
+  }
+
   void define_tristan(py::module& m) {
     define_tristan_d<1>(m);
     define_tristan_d<2>(m);

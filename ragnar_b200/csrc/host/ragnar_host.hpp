@@ -84,6 +84,8 @@ namespace rgb {
     py::array_t<T> as_array() const;
     const T*    host_data() const; // cached host mirror (extent(0) elements)
     std::size_t extent(unsigned short d = 0) const;
+    // the C-ABI handle behind this array (nullptr for an empty array)
+    rgc_buf_t* handle() const { return m_store ? m_store->dev : nullptr; }
   };
 
   // reference src/containers/bins.hpp:17-33
@@ -263,7 +265,8 @@ namespace rgb {
   void define_generators(py::module& m);
   void define_particles(py::module& m);
   void define_synchrotron(py::module& m);
-  void define_not_yet(py::module& m); // ICSpectrum, H5read/write
+  void define_h5(py::module& m);      // H5read1DArray_* / H5write1DArray_*
+  void define_not_yet(py::module& m); // ICSpectrum
   void define_tristan(py::module& m);
 
 } // namespace rgb

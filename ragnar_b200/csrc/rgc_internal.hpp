@@ -84,6 +84,9 @@ namespace rgc {
   int allreduce_sum_f64(double* dev, std::size_t n);
   int allreduce_sum_u64(unsigned long long* dev, std::size_t n);
 
+  // frees the pinned I/O lanes of the HDF5 streaming reader (rgc_tristan.cpp)
+  void io_release_lanes();
+
   // host -> device copy that accepts pageable or pinned sources (see rgc_runtime.cu)
   int copy_h2d(void* dst, const void* src, std::size_t bytes, cudaStream_t stream);
 

@@ -255,6 +255,7 @@ extern "C" {
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
     rgc_comm_destroy();
+    io_release_lanes();
     for (int s = 0; s < kNumStages; ++s) {
       if (c.stage[s]) {
         cudaFreeHost(c.stage[s]);
