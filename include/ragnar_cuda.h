@@ -206,6 +206,19 @@ int rgc_sync_spectrum_dist(const float* gbeta, const float* f, size_t ndist,
                            const float* tab_x, const float* tab_y, size_t tab_n, float g_syn,
                            float e_syn_at_g_syn, float* out_spec, double* out_spec64);
 
+/* ICSpectrum + ic::Kernel + ic::KNfunc — src/physics/ic.cpp:15-46,
+ * src/physics/ic.hpp:20-85.  (g_prtls, f_prtls): particle TabulatedDistribution;
+ * (e_soft, f_soft): soft-photon TabulatedDistribution (mec^2); bins_e_ic: nic IC
+ * energies.  out[j] = sum over (g, s) of the reference's float term, summed in fp64
+ * (out_spec64) and rounded once to float (out_spec); either may be NULL.  The unit
+ * checks of ic::Kernel's constructor (ic.hpp:48-55) live in the host wrapper, which
+ * owns the Bins' units.  Index intent, not the reference's swapped MDRange extents
+ * (see rgc_ic.cu); identical when nsoft == nic.  Replicated, never all-reduced. */
+int rgc_ic_spectrum(const float* g_prtls, const float* f_prtls, size_t nprtls,
+                    int islog_bins_prtls, const float* e_soft, const float* f_soft,
+                    size_t nsoft, const float* bins_e_ic, size_t nic, float* out_spec,
+                    double* out_spec64);
+
 /* Device time (ms, CUDA events on the compute stream) of the kernels of the last
  * hot-path call on this thread: [0] total, [1] dominant kernel only. */
 int rgc_last_kernel_ms(float ms[2]);

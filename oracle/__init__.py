@@ -128,6 +128,9 @@ class _Port:
                 _f32p, _f32p, ctypes.c_size_t, ctypes.c_int, _f32p, ctypes.c_size_t,
                 _f32p, _f32p, ctypes.c_size_t, ctypes.c_float, ctypes.c_float,
                 _f32p, _f64p]
+            lib.orc_ic_spectrum.argtypes = [
+                _f32p, _f32p, ctypes.c_size_t, ctypes.c_int, _f32p, _f32p, ctypes.c_size_t,
+                _f32p, ctypes.c_size_t, _f32p, _f64p]
             self._lib = lib
         return self._lib
 
@@ -228,6 +231,15 @@ class _Port:
         self.lib.orc_sync_spectrum_dist(_p(gbeta), _p(f), len(gbeta), int(islog), _p(bins),
                                         len(bins), _p(tx), _p(ty), len(tx), g_syn, e_at,
                                         _p(s32), _p(s64, _f64p))
+        return s32, s64
+
+    def ic_spectrum(self, g_prtls, f_prtls, islog, e_soft, f_soft, bins_e_ic):
+        """-> (spec_f32 faithful serial order, spec_f64)"""
+        g, f, es, fs, b = (_f32(a) for a in (g_prtls, f_prtls, e_soft, f_soft, bins_e_ic))
+        s32 = np.zeros(len(b), np.float32)
+        s64 = np.zeros(len(b), np.float64)
+        self.lib.orc_ic_spectrum(_p(g), _p(f), len(g), int(islog), _p(es), _p(fs), len(es),
+                                 _p(b), len(b), _p(s32), _p(s64, _f64p))
         return s32, s64
 
     def num_threads(self) -> int:

@@ -73,6 +73,8 @@ SIGNATURES = {
                                               C.c_float, C.c_float, C.c_float, _f32p, _f64p]),
     "rgc_sync_spectrum_dist": (C.c_int, [_f32p, _f32p, _sz, C.c_int, _f32p, _sz, _f32p, _f32p,
                                          _sz, C.c_float, C.c_float, _f32p, _f64p]),
+    "rgc_ic_spectrum": (C.c_int, [_f32p, _f32p, _sz, C.c_int, _f32p, _f32p, _sz, _f32p, _sz,
+                                  _f32p, _f64p]),
     "rgc_last_kernel_ms": (C.c_int, [_f32p]),
     "rgc_last_kernel_times": (C.c_int, [_f32p, C.c_int]),
     "rgc_measure_peak": (C.c_int, [C.c_int, _f64p, _f64p]),
@@ -373,6 +375,18 @@ def sync_spectrum_dist(gbeta, f, islog, bins_e_syn, g_syn, e_at, table=None):
     check(lib().rgc_sync_spectrum_dist(_ptr(gbeta), _ptr(f), len(gbeta), int(islog), _ptr(bins),
                                        len(bins), _ptr(tx), _ptr(ty), len(tx), g_syn, e_at,
                                        _ptr(s32), _ptr(s64, _f64p)))
+    return s32, s64
+
+
+def ic_spectrum(g_prtls, f_prtls, islog, e_soft, f_soft, bins_e_ic):
+    """ICSpectrum (reference src/physics/ic.cpp:15-46) -> (spec_f32, spec_f64)"""
+    g, f, es, fs, b = (_f32(a) for a in (g_prtls, f_prtls, e_soft, f_soft, bins_e_ic))
+    if len(g) != len(f) or len(es) != len(fs):
+        raise ValueError("distribution arrays of unequal length")
+    s32 = np.zeros(len(b), np.float32)
+    s64 = np.zeros(len(b), np.float64)
+    check(lib().rgc_ic_spectrum(_ptr(g), _ptr(f), len(g), int(islog), _ptr(es), _ptr(fs), len(es),
+                                _ptr(b), len(b), _ptr(s32), _ptr(s64, _f64p)))
     return s32, s64
 
 

@@ -42,5 +42,5 @@ PYBIND11_MODULE(ragnar, m) {
   rgb::define_tristan(m);
   rgb::define_generators(m);
   rgb::define_synchrotron(m);
-  rgb::define_not_yet(m);
+  rgb::define_ic(m);
 }

@@ -100,17 +100,38 @@ namespace rgb {
           "bins_e_syn"_a, "g_syn"_a, "e_syn_at_g_syn"_a, doc::SynchrotronSpectrumFromDist);
   }
 
-  // exported with the reference's signature and docstring,
-  // not implemented yet (there is no CPU path to route it to)
-  void define_not_yet(py::module& m) {
-    m.def(
-      "ICSpectrum",
-      [](const TabulatedDistribution&, const TabulatedDistribution&, const Bins&) -> Array1D<real_t> {
-        PyErr_SetString(PyExc_NotImplementedError,
-                        "ICSpectrum is outside the B200 hot path of this build (SURVEY.md 8f-f1)");
-        throw py::error_already_set();
-      },
-      "dist_prtls"_a, "dist_soft_photons"_a, "bins_e_ic"_a, doc::ICSpectrum);
+  // reference src/physics/ic.cpp:15-46.  ic::Kernel's constructor (ic.hpp:48-55) is
+  // evaluated as an argument of parallel_for, i.e. after the " Launching" line: the
+  // unit errors surface there too.
+  Array1D<real_t> ICSpectrum(const TabulatedDistribution& dist_prtls,
+                             const TabulatedDistribution& dist_soft_photons,
+                             const Bins&                  bins_e_ic) {
+    py::print("Computing IC spectrum ...", "flush"_a = true);
+    const auto nbins_prtls        = dist_prtls.extent();
+    const auto nbins_soft_photons = dist_soft_photons.extent();
+    const auto nbins_ic           = bins_e_ic.extent(0);
+    py::print(" Launching",
+              human_readable((double)(nbins_prtls * nbins_soft_photons * nbins_ic)), "threads",
+              "end"_a = "", "flush"_a = true);
+    if (dist_soft_photons.EnergyBins().unit != EnergyUnits::mec2) {
+      throw std::runtime_error("Soft photons energy bins must be in units of mec^2");
+    }
+    if (bins_e_ic.unit != EnergyUnits::mec2) {
+      throw std::runtime_error("E_ic must be in units of mec^2");
+    }
+    std::vector<real_t> spec(nbins_ic, 0.0f);
+    check(rgc_ic_spectrum(dist_prtls.EnergyBins().host_data(), dist_prtls.F().host_data(),
+                          nbins_prtls, dist_prtls.log_spaced() ? 1 : 0,
+                          dist_soft_photons.EnergyBins().host_data(),
+                          dist_soft_photons.F().host_data(), nbins_soft_photons,
+                          bins_e_ic.host_data(), nbins_ic, spec.data(), nullptr));
+    py::print(": OK", "flush"_a = true);
+    return Array1D<real_t> { spec };
+  }
+
+  void define_ic(py::module& m) {
+    m.def("ICSpectrum", &ICSpectrum, "dist_prtls"_a, "dist_soft_photons"_a, "bins_e_ic"_a,
+          doc::ICSpectrum);
   }
 
 } // namespace rgb

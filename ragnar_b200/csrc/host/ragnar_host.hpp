@@ -266,7 +266,7 @@ namespace rgb {
   void define_particles(py::module& m);
   void define_synchrotron(py::module& m);
   void define_h5(py::module& m);      // H5read1DArray_* / H5write1DArray_*
-  void define_not_yet(py::module& m); // ICSpectrum
+  void define_ic(py::module& m); // ICSpectrum (reference src/physics/ic.cpp)
   void define_tristan(py::module& m);
 
 } // namespace rgb

@@ -7,7 +7,8 @@ import subprocess
 import sys
 
 rep, units = sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+sel = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", *sel], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr, data = rows[hdr_i], rows[hdr_i + 1:]
