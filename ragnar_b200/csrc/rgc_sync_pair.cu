@@ -1,5 +1,5 @@
 // Bucketed hinge form of the particle synchrotron spectrum for sm_100a — the
-// FP32-pipe-bound main kernel of SynchrotronSpectrum_<D>D.
+// FP32-pipe-bound main path of SynchrotronSpectrum_<D>D.
 //
 // Replaces (reference paths relative to haykh/ragnar @ fceb6b08):
 //   sync::Kernel<D>::operator() / OmegaSync_ChiR   src/physics/synchrotron.hpp:145-232
@@ -16,33 +16,46 @@
 // over the bucket's particles with weights w_i = chiR_i:
 //     sum_i w_i F_ij = v_q S0 + s_q (fa_j S0 + S1) + ds_q * sum_i w_i max(0, fa_j - h_q + fc_i)
 // S0 = sum w_i and S1 = sum w_i fc_i do not depend on the bin; only the hinge
-// needs per-pair work:  r = sat(fa'_j + fc_i);  S2_j += w_i * r   — one FADD.SAT
+// needs per-pair work:  r = sat(fa'_j + fc_i);  S2_j += w_i * r   — one FFMA.SAT
 // and one FFMA per (particle, bin) evaluation, nothing else in the inner loop.
 // (The upper clamp of .SAT never binds for real bins: fa' + fc < 1 + |h - 1|.)
 // Two spare lanes per warp column run the same instructions with fa' = 1 and
 // fa' = 0 and so deliver S0 and S1 for free.
 //
-// One CTA owns a tile of 4096 particles at a time:
-//   pass 1  prologue per particle (gamma, beta, chiR, e_peak with the reference's
-//           fp64 promotions) -> (bucket, fc, w) staged in shared memory, per-warp
-//           bucket counts
-//   scan    bucket offsets (each bucket padded to an even length with one
-//           zero-weight entry), per-warp cursors
-//   pass 2  warp-synchronous stable ranking (MATCH.ANY) -> bucket-sorted (fc, w)
-//   pairs   the sorted range is split evenly over the warp rows; a warp walks its
-//           range bucket by bucket: loads (ds, h) of its lanes' cells once per
-//           segment, then runs the 2-instruction pair loop from broadcast LDS.128
-// Hinge sums are float per segment, folded into fp64 per tile; bucket moments
-// are fp64 per CTA; all reductions run in a fixed order: bitwise reproducible.
-// The linear part  v_q S0 + s_q (fa_j S0 + S1)  is added once, in fp64, by the
-// final reduction kernel from the moments summed over CTAs.
+// Pipeline (one pass per <= 2^27 particles), all on the compute stream:
+//   1 sync_prologue_kernel  HBM-bound (36 B read, 10 B written per particle):
+//       gamma, beta, chiR, e_peak with the reference's fp64 promotions ->
+//       (fc, w) and the bucket key, in particle order; bucket counts per row (a row
+//       is a contiguous range of 4096-particle tiles, one row per CTA of kernel 3)
+//       from a shared-memory histogram flushed by integer atomics
+//   2 pair_colscan_kernel   counts[bucket][row] -> exclusive offsets inside the
+//       bucket + bucket totals (one warp per bucket)
+//   3 sync_sort_kernel      HBM-bound (10 B read, 8 B written): a CTA walks its row
+//       tile by tile: TMA bulk copy of the tile's (fc, w, key) into shared memory,
+//       warp-synchronous stable ranking (ballot match), scan, scatter to bucket
+//       order INSIDE shared memory, then coalesced write-out of every bucket run to
+//       its place in the GLOBAL bucket order (scattered 8-byte global stores cost
+//       ~5 clk each per SM; runs of a tile are contiguous).  Row order x tile order
+//       x (warp, step, lane) order: deterministic.
+//   4 sync_pair_kernel      FP32-bound: the sorted array is cut into pieces of
+//       <= 1024 entries of one bucket; a warp takes pieces round-robin, loads the
+//       (ds, h) of its lanes' cells once per piece and streams the piece through a
+//       warp-private ring of TMA bulk copies (4 x 512 B, mbarrier per stage) into
+//       the 2-instruction pair loop fed by broadcast LDS.128.  No CTA barrier
+//       inside the loop.
+//   5 pair_moments_kernel / pair_final_kernel   fp64 bucket moments from the
+//       pieces' spare-lane sums, CTA partials + the linear part
+//       v_q S0 + s_q (fa_j S0 + S1)  ->  one value per bin.
+// Hinge sums are float per piece, folded into fp64 per piece; every reduction
+// runs in a fixed order: bitwise reproducible.
 //
 // Requires a table with F = 0 at both ends (true for sync::TabulateFfunc, whose
 // first node is forced to 0 and whose nodes beyond x = 20 are 0); any other table,
 // very wide bin ranges and the FromDist form use the gather kernel.
 //
 // Roofline: 2 FP32-pipe instructions per evaluation against the measured FFMA issue
-// rate (rgc_measure_peak kind 0/1); HBM: 36 B per particle amortised over nbins.
+// rate (rgc_measure_peak kind 0/1); HBM: 64 B per particle over the three streaming
+// kernels, amortised over nbins.
 //
 // Compiled with -fmad=false: every FMA below is an explicit fmaf()/fma().
 #include "rgc_internal.hpp"
@@ -55,15 +68,17 @@
 
 namespace rgc {
 
-  constexpr int kPThreads  = 256;
-  constexpr int kPWarps    = kPThreads / 32;
-  constexpr int kPTile     = 4096; // particles per CTA tile (16 per thread)
-  constexpr int kPSteps    = kPTile / kPThreads;
-  constexpr int kPMaxGPW   = 8;
-  constexpr int kPMaxBins  = 8 * (kPMaxGPW * 32 - 2); // 2032 per launch
+  constexpr int kPThreads    = 256;
+  constexpr int kPWarps      = kPThreads / 32;
+  constexpr int kPMaxGPW     = 8;
+  constexpr int kPMaxBins    = 8 * (kPMaxGPW * 32 - 2); // 2032 per launch
   constexpr int kPMaxBuckets = 1024;
   constexpr unsigned kInvalidKey = 0xffffu;
-  constexpr int kSegCostDefault = 16; // per-segment overhead of the pair phase, in sorted entries
+  constexpr int kPTile       = 4096; // particles per tile of the prologue / sort kernels
+  constexpr int kPSteps      = kPTile / kPThreads;
+  constexpr int kPieceLen    = 1024; // sorted entries per work unit of the pair kernel
+  constexpr int kStageLen    = 64;   // sorted entries per TMA stage (512 B)
+  constexpr int kStages      = 4;    // ring depth per warp
 
   struct PairParams {
     const float* u[3];
@@ -80,46 +95,38 @@ namespace rgc {
     double e_scale;          // e_syn_at_g_syn / (g_syn * g_syn), the float product promoted
     double cells_per_octave; // log10(2) / dL
     double c0, inv_dL, c_lo, c_hi;
-    // staged per-particle results of the prologue kernel, padded to whole tiles
+    // staged per-particle results of the prologue kernel (particle order)
     float2*         cw;   // (fc, w)
     unsigned short* keys; // bucket, kInvalidKey = not on the table
-    std::size_t     npad; // ntiles * kPTile
-    double* partials; // [cta][nslots] hinge sums
-    double* moments;  // [cta][2 * nb]  S0 then S1 per bucket
-    int     nslots;
-    int     seg_cost; // cost-model weight of one bucket segment, in sorted entries
-    // shared-memory layout (byte offsets, computed once on the host)
-    int o_coef, o_s0tot, o_s1tot, o_start, o_cstart, o_hw, o_stage_cw, o_stage_k, o_sorted, o_edge, o_scan, o_mbar, o_seg_s0, o_seg_s1;
-  };
-
-  struct PairEdge {
-    int   b;
-    float s0, s1;
+    // rows: row r owns tiles [r * tiles_per_row, (r + 1) * tiles_per_row) of kPTile particles
+    int         rows, ntiles, tiles_per_row, tiles_per_cta1;
+    int*        counts; // [nbp][rows]: per-row bucket counts, then offsets inside the bucket
+    int*        tot;    // [nbp] valid particles per bucket
+    float2*     sorted; // (fc, w) in global bucket order, every bucket padded to an even length
+    float2*     piece_mom; // [piece] {S0, S1} of the piece (float sums of <= kPieceLen terms)
+    double*     partials;  // [cta][nslots] hinge sums
+    int         nslots;
+    // shared-memory layout of the pair kernel (byte offsets, computed once on the host)
+    int o_coef, o_bstart, o_pstart, o_tmp, o_ring, o_mbar, o_red;
   };
 
   __host__ __device__ inline std::size_t pair_align16(std::size_t x) { return (x + 15) & ~std::size_t(15); }
 
   struct PairSmem {
-    std::size_t coef, s0tot, s1tot, start, cstart, seg_s0, seg_s1, hw, stage_cw, stage_k, sorted, edge, scan, mbar, total;
+    std::size_t coef, bstart, pstart, tmp, ring, mbar, red, total;
   };
 
-  __host__ __device__ inline PairSmem pair_smem_layout(int n_pad, int nb, int nbp) {
+  __host__ __device__ inline PairSmem pair_smem_layout(int n_pad, int nbp, int gpw) {
     PairSmem L;
     std::size_t o = 0;
-    L.coef = o;      o = pair_align16(o + (std::size_t)n_pad * sizeof(float4));
-    L.s0tot = o;     o = pair_align16(o + (std::size_t)nb * sizeof(double));
-    L.s1tot = o;     o = pair_align16(o + (std::size_t)nb * sizeof(double));
-    L.start = o;     o = pair_align16(o + (std::size_t)(nb + 2) * sizeof(int));
-    L.cstart = o;    o = pair_align16(o + (std::size_t)(nb + 2) * sizeof(int));
-    L.seg_s0 = o;    o = pair_align16(o + (std::size_t)(nb + 2) * sizeof(float));
-    L.seg_s1 = o;    o = pair_align16(o + (std::size_t)(nb + 2) * sizeof(float));
-    L.hw = o;        o = pair_align16(o + (std::size_t)kPWarps * nbp * sizeof(unsigned short));
-    L.stage_cw = o;  o = pair_align16(o + (std::size_t)kPTile * sizeof(float2));
-    L.stage_k = o;   o = pair_align16(o + (std::size_t)kPTile * sizeof(unsigned short));
-    L.sorted = o;    o = pair_align16(o + (std::size_t)(kPTile + nb + 10) * sizeof(float2));
-    L.edge = o;      o = pair_align16(o + (std::size_t)kPWarps * 2 * sizeof(PairEdge));
-    L.scan = o;      o = pair_align16(o + (std::size_t)(2 * kPWarps + 1) * sizeof(int));
-    L.mbar = o;      o = pair_align16(o + 16);
+    L.coef = o;    o = pair_align16(o + (std::size_t)n_pad * sizeof(float4));
+    L.bstart = o;  o = pair_align16(o + (std::size_t)(nbp + 2) * sizeof(int));
+    L.pstart = o;  o = pair_align16(o + (std::size_t)(nbp + 2) * sizeof(int));
+    L.tmp = o;     o = pair_align16(o + (std::size_t)(2 * kPWarps) * sizeof(int));
+    o = (o + 127) & ~std::size_t(127);
+    L.ring = o;    o = pair_align16(o + (std::size_t)kPWarps * kStages * kStageLen * sizeof(float2));
+    L.mbar = o;    o = pair_align16(o + (std::size_t)kPWarps * kStages * 8);
+    L.red = o;     o = pair_align16(o + (std::size_t)kPWarps * gpw * 32 * sizeof(double));
     L.total = o;
     return L;
   }
@@ -267,129 +274,251 @@ namespace rgc {
     return m;
   }
 
+  // Exclusive scans over the buckets, by one CTA of kPThreads threads:
+  //   bstart[b] = first sorted entry of bucket b (every bucket padded to an even length)
+  //   pstart[b] = first piece of bucket b (pieces of kPieceLen entries, the last one short)
+  // entries [0, nb]; tmp: 2 * kPWarps ints.  Ends with a __syncthreads().
+  __device__ __forceinline__ void block_scan_buckets(const int* __restrict__ tot, int nb,
+                                                     int* bstart, int* pstart, int* tmp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kPer = kPMaxBuckets / kPThreads; // 4 consecutive buckets per thread
+    int pe[kPer], pp[kPer];
+    int esum = 0, psum = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int b   = tid * kPer + i;
+      const int t   = b < nb ? tot[b] : 0;
+      const int pad = (t + 1) & ~1;
+      pe[i]         = pad;
+      pp[i]         = (pad + kPieceLen - 1) / kPieceLen;
+      esum += pad;
+      psum += pp[i];
+    }
+    int ei = esum, pi = psum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int te = __shfl_up_sync(0xffffffffu, ei, off);
+      const int tp = __shfl_up_sync(0xffffffffu, pi, off);
+      if (lane >= off) {
+        ei += te;
+        pi += tp;
+      }
+    }
+    if (lane == 31) {
+      tmp[warp]           = ei;
+      tmp[kPWarps + warp] = pi;
+    }
+    __syncthreads();
+    int ebase = 0, pbase = 0;
+#pragma unroll
+    for (int wq = 0; wq < kPWarps; ++wq) {
+      ebase += wq < warp ? tmp[wq] : 0;
+      pbase += wq < warp ? tmp[kPWarps + wq] : 0;
+    }
+    int erun = ebase + ei - esum, prun = pbase + pi - psum;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int b = tid * kPer + i;
+      if (b <= nb) {
+        bstart[b] = erun;
+        pstart[b] = prun;
+      }
+      erun += pe[i];
+      prun += pp[i];
+    }
+    __syncthreads();
+  }
+
   // ---- kernel 1: per-particle prologue, streamed once over the particle columns
-  // (36 B read, 10 B written per particle; HBM-bound).  Entries past nprtl up to the
-  // end of the last tile are written as invalid so the pair kernel copies whole tiles.
+  // (36 B read, 10 B written per particle; HBM-bound), plus the bucket counts of
+  // every row.  A CTA owns a contiguous range of tiles; its shared-memory histogram
+  // is added to the row's global counts (integer atomics: order-independent) whenever
+  // the row changes.  Entries past nprtl up to the end of the last tile are written
+  // as invalid so the sort kernel copies whole tiles.
   template <int MINB>
-  __global__ void __launch_bounds__(256, MINB)
+  __global__ void __launch_bounds__(kPThreads, MINB)
     sync_prologue_kernel(const __grid_constant__ PairParams P) {
-    const std::size_t stride = (std::size_t)gridDim.x * blockDim.x * 4;
-    for (std::size_t i0 = ((std::size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < P.npad;
-         i0 += stride) {
-      float4 v[9];
-      if (i0 < P.nprtl) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          v[d]     = __ldcs(reinterpret_cast<const float4*>(P.u[d] + i0));
-          v[3 + d] = __ldcs(reinterpret_cast<const float4*>(P.e[d] + i0));
-          v[6 + d] = __ldcs(reinterpret_cast<const float4*>(P.b[d] + i0));
+    __shared__ int hist[kPMaxBuckets];
+    const int      tid = threadIdx.x;
+    for (int i = tid; i < P.nbp; i += kPThreads) {
+      hist[i] = 0;
+    }
+    __syncthreads();
+    const int t0 = blockIdx.x * P.tiles_per_cta1;
+    const int t1 = min(t0 + P.tiles_per_cta1, P.ntiles);
+    auto flush = [&](int row) {
+      __syncthreads();
+      for (int b = tid; b < P.nb; b += kPThreads) {
+        const int v = hist[b];
+        if (v) {
+          atomicAdd(&P.counts[(std::size_t)b * P.rows + row], v);
+          hist[b] = 0;
         }
       }
-      const float*   f = reinterpret_cast<const float*>(v);
-      float          out_cw[8];
-      unsigned short out_k[4];
+      __syncthreads();
+    };
+    for (int tile = t0; tile < t1; ++tile) {
+      const std::size_t base = (std::size_t)tile * kPTile;
+#pragma unroll 1
+      for (int step = 0; step < kPTile / (kPThreads * 4); ++step) {
+        const std::size_t i0 = base + (std::size_t)step * (kPThreads * 4) + (std::size_t)tid * 4;
+        float4            v[9];
+        if (i0 < P.nprtl) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        unsigned bucket = kInvalidKey;
-        float    fc = 0.0f, w = 0.0f;
-        bool     ok = false;
-        if (i0 + k < P.nprtl) {
-          ok = pair_prologue(P, f[0 * 4 + k], f[1 * 4 + k], f[2 * 4 + k], f[3 * 4 + k],
-                             f[4 * 4 + k], f[5 * 4 + k], f[6 * 4 + k], f[7 * 4 + k],
-                             f[8 * 4 + k], bucket, fc, w);
+          for (int d = 0; d < 3; ++d) {
+            v[d]     = __ldcs(reinterpret_cast<const float4*>(P.u[d] + i0));
+            v[3 + d] = __ldcs(reinterpret_cast<const float4*>(P.e[d] + i0));
+            v[6 + d] = __ldcs(reinterpret_cast<const float4*>(P.b[d] + i0));
+          }
         }
-        out_k[k]          = (unsigned short)(ok ? bucket : kInvalidKey);
-        out_cw[2 * k]     = ok ? fc : 0.0f;
-        out_cw[2 * k + 1] = ok ? w : 0.0f;
+        const float*   f = reinterpret_cast<const float*>(v);
+        float          out_cw[8];
+        unsigned short out_k[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          unsigned bucket = kInvalidKey;
+          float    fc = 0.0f, w = 0.0f;
+          bool     ok = false;
+          if (i0 + k < P.nprtl) {
+            ok = pair_prologue(P, f[0 * 4 + k], f[1 * 4 + k], f[2 * 4 + k], f[3 * 4 + k],
+                               f[4 * 4 + k], f[5 * 4 + k], f[6 * 4 + k], f[7 * 4 + k],
+                               f[8 * 4 + k], bucket, fc, w);
+          }
+          out_k[k]          = (unsigned short)(ok ? bucket : kInvalidKey);
+          out_cw[2 * k]     = ok ? fc : 0.0f;
+          out_cw[2 * k + 1] = ok ? w : 0.0f;
+          if (ok) {
+            atomicAdd(&hist[bucket], 1);
+          }
+        }
+        float4* cw4 = reinterpret_cast<float4*>(P.cw + i0);
+        cw4[0]      = make_float4(out_cw[0], out_cw[1], out_cw[2], out_cw[3]);
+        cw4[1]      = make_float4(out_cw[4], out_cw[5], out_cw[6], out_cw[7]);
+        *reinterpret_cast<uint2*>(P.keys + i0) =
+          make_uint2((unsigned)out_k[0] | ((unsigned)out_k[1] << 16),
+                     (unsigned)out_k[2] | ((unsigned)out_k[3] << 16));
       }
-      float4* cw4 = reinterpret_cast<float4*>(P.cw + i0);
-      cw4[0]      = make_float4(out_cw[0], out_cw[1], out_cw[2], out_cw[3]);
-      cw4[1]      = make_float4(out_cw[4], out_cw[5], out_cw[6], out_cw[7]);
-      *reinterpret_cast<uint2*>(P.keys + i0) =
-        make_uint2((unsigned)out_k[0] | ((unsigned)out_k[1] << 16),
-                   (unsigned)out_k[2] | ((unsigned)out_k[3] << 16));
+      if (tile + 1 == t1 || (tile + 1) / P.tiles_per_row != tile / P.tiles_per_row) {
+        flush(tile / P.tiles_per_row);
+      }
     }
   }
 
-  // ---- kernel 2: bucket sort inside the tile + the pair loop
-  template <int GPW>
+  // ---- kernel 2: per bucket (one warp each), exclusive scan of the row counts in
+  // row order -> offset of every row's first particle inside the bucket; bucket totals
+  __global__ void __launch_bounds__(kPThreads)
+    pair_colscan_kernel(int* __restrict__ counts, int rows, int nb, int* __restrict__ tot) {
+    const int lane = threadIdx.x & 31;
+    const int b    = blockIdx.x * kPWarps + (threadIdx.x >> 5);
+    if (b >= nb) {
+      return;
+    }
+    int* col = counts + (std::size_t)b * rows;
+    int  run = 0;
+#pragma unroll 4
+    for (int r0 = 0; r0 < rows; r0 += 32) {
+      const int r    = r0 + lane;
+      const int v    = r < rows ? col[r] : 0;
+      int       incl = v;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) {
+          incl += t;
+        }
+      }
+      if (r < rows) {
+        col[r] = run + incl - v;
+      }
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+      tot[b] = run;
+    }
+  }
+
+  struct SortSmem {
+    std::size_t bstart, pstart, tmp, gcur, seg_off, hw, stage_cw, stage_k, sorted, sorted_k, mbar, total;
+  };
+
+  __host__ __device__ inline SortSmem sort_smem_layout(int nbp) {
+    SortSmem    L;
+    std::size_t o = 0;
+    L.bstart = o;   o = pair_align16(o + (std::size_t)(nbp + 2) * sizeof(int));
+    L.pstart = o;   o = pair_align16(o + (std::size_t)(nbp + 2) * sizeof(int));
+    L.tmp = o;      o = pair_align16(o + (std::size_t)(2 * kPWarps + 2) * sizeof(int));
+    L.gcur = o;     o = pair_align16(o + (std::size_t)nbp * sizeof(int));
+    L.seg_off = o;  o = pair_align16(o + (std::size_t)(nbp + 2) * sizeof(int));
+    L.hw = o;       o = pair_align16(o + (std::size_t)kPWarps * nbp * sizeof(unsigned short));
+    o = (o + 127) & ~std::size_t(127);
+    L.stage_cw = o; o = pair_align16(o + (std::size_t)kPTile * sizeof(float2));
+    L.stage_k = o;  o = pair_align16(o + (std::size_t)kPTile * sizeof(unsigned short));
+    L.sorted = o;   o = pair_align16(o + (std::size_t)kPTile * sizeof(float2));
+    L.sorted_k = o; o = pair_align16(o + (std::size_t)kPTile * sizeof(unsigned short));
+    L.mbar = o;     o = pair_align16(o + 16);
+    L.total = o;
+    return L;
+  }
+
+  // ---- kernel 3: bucket sort of every tile inside shared memory, coalesced write-out
+  // of the tile's bucket runs into the global bucket order.  One CTA per row.
   __global__ void __launch_bounds__(kPThreads, 2)
-    sync_pair_kernel(const __grid_constant__ PairParams P) {
+    sync_sort_kernel(const __grid_constant__ PairParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4*         coef     = reinterpret_cast<float4*>(smem_raw + P.o_coef);
-    double*         s0tot    = reinterpret_cast<double*>(smem_raw + P.o_s0tot);
-    double*         s1tot    = reinterpret_cast<double*>(smem_raw + P.o_s1tot);
-    int*            seg_start = reinterpret_cast<int*>(smem_raw + P.o_start);   // [nb + 2]
-    int*            seg_b     = reinterpret_cast<int*>(smem_raw + P.o_cstart);  // [nb + 2]
-    float*          seg_s0    = reinterpret_cast<float*>(smem_raw + P.o_seg_s0);
-    float*          seg_s1    = reinterpret_cast<float*>(smem_raw + P.o_seg_s1);
-    unsigned short* hw16     = reinterpret_cast<unsigned short*>(smem_raw + P.o_hw);
-    unsigned*       hw32     = reinterpret_cast<unsigned*>(smem_raw + P.o_hw);
-    float2*         stage_cw = reinterpret_cast<float2*>(smem_raw + P.o_stage_cw);
-    unsigned short* stage_k  = reinterpret_cast<unsigned short*>(smem_raw + P.o_stage_k);
-    float2*         sorted   = reinterpret_cast<float2*>(smem_raw + P.o_sorted);
-    PairEdge*       edge     = reinterpret_cast<PairEdge*>(smem_raw + P.o_edge);
-    int*            scan_tmp = reinterpret_cast<int*>(smem_raw + P.o_scan);
-    void*           mbar     = smem_raw + P.o_mbar;
+    const SortSmem  L        = sort_smem_layout(P.nbp);
+    int*            bstart   = reinterpret_cast<int*>(smem_raw + L.bstart);
+    int*            pstart   = reinterpret_cast<int*>(smem_raw + L.pstart);
+    int*            scan_tmp = reinterpret_cast<int*>(smem_raw + L.tmp);
+    int*            gcur     = reinterpret_cast<int*>(smem_raw + L.gcur);
+    int*            seg_off  = reinterpret_cast<int*>(smem_raw + L.seg_off);
+    unsigned short* hw16     = reinterpret_cast<unsigned short*>(smem_raw + L.hw);
+    unsigned*       hw32     = reinterpret_cast<unsigned*>(smem_raw + L.hw);
+    float2*         stage_cw = reinterpret_cast<float2*>(smem_raw + L.stage_cw);
+    unsigned short* stage_k  = reinterpret_cast<unsigned short*>(smem_raw + L.stage_k);
+    float2*         sorted   = reinterpret_cast<float2*>(smem_raw + L.sorted);
+    unsigned short* sorted_k = reinterpret_cast<unsigned short*>(smem_raw + L.sorted_k);
+    void*           mbar     = smem_raw + L.mbar;
 
     const int tid  = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int col  = warp % P.ncols;
-    const int row  = warp / P.ncols;
-    const int rows = kPWarps / P.ncols;
     const int nb   = P.nb;
     const int nbp  = P.nbp;
+    const int row  = blockIdx.x;
+    const int t0   = row * P.tiles_per_row;
+    const int t1   = min(t0 + P.tiles_per_row, P.ntiles);
 
-    const std::size_t ntiles = P.npad / kPTile;
     constexpr unsigned kStageBytesCW = kPTile * sizeof(float2);
     constexpr unsigned kStageBytesK  = kPTile * sizeof(unsigned short);
-    // the staged (fc, w, key) of a tile arrive by TMA bulk copy; the copy of the next
-    // tile is issued as soon as the sort no longer reads the staging buffers, so it
-    // lands underneath the pair loop
-    auto issue_tile_copy = [&](std::size_t tile) {
+    auto issue_tile_copy = [&](int tile) {
       mbar_expect_tx(mbar, kStageBytesCW + kStageBytesK);
-      bulk_g2s(stage_cw, P.cw + tile * kPTile, kStageBytesCW, mbar);
-      bulk_g2s(stage_k, P.keys + tile * kPTile, kStageBytesK, mbar);
+      bulk_g2s(stage_cw, P.cw + (std::size_t)tile * kPTile, kStageBytesCW, mbar);
+      bulk_g2s(stage_k, P.keys + (std::size_t)tile * kPTile, kStageBytesK, mbar);
     };
     if (tid == 0) {
       mbar_init(mbar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < P.n_pad; i += kPThreads) {
-      coef[i] = P.coef_dh[i];
+    block_scan_buckets(P.tot, nb, bstart, pstart, scan_tmp); // ends with __syncthreads()
+    if (tid == 0 && t0 < t1) {
+      issue_tile_copy(t0);
     }
-    for (int i = tid; i < nb; i += kPThreads) {
-      s0tot[i] = 0.0;
-      s1tot[i] = 0.0;
+    if (row == 0) {
+      for (int b = tid; b < nb; b += kPThreads) {
+        const int t = P.tot[b];
+        if (t & 1) {
+          P.sorted[bstart[b] + t] = make_float2(0.0f, 0.0f); // zero-weight pad of the bucket
+        }
+      }
     }
-    if (tid < kPWarps * 2) {
-      edge[tid].b = -1;
-    }
-    __syncthreads();
-    if (tid == 0 && blockIdx.x < ntiles) {
-      issue_tile_copy(blockIdx.x);
-    }
-
-    int    aoff[GPW];
-    float  fa0[GPW], acc[GPW];
-    double accd[GPW];
-#pragma unroll
-    for (int g = 0; g < GPW; ++g) {
-      const int    slot = (col * GPW + g) * 32 + lane;
-      const int2   si   = P.slot_i[slot];
-      const float2 sf   = P.slot_f[slot];
-      aoff[g] = si.x;
-      fa0[g]  = sf.x;
-      acc[g]  = 0.0f;
-      accd[g] = 0.0;
+    for (int b = tid; b < nb; b += kPThreads) {
+      gcur[b] = bstart[b] + P.counts[(std::size_t)b * P.rows + row];
     }
 
-    const int bpt    = (nb + kPThreads - 1) / kPThreads; // buckets per thread in the scan
-    unsigned  parity = 0;
-
-    for (std::size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      // ---- per-warp bucket cursors (u16), zeroed; the previous tile's pair phase is
+    constexpr int kPer = kPMaxBuckets / kPThreads; // buckets per thread in the scan
+    unsigned      parity = 0;
+    for (int tile = t0; tile < t1; ++tile) {
+      // ---- per-warp bucket cursors (u16), zeroed; the previous tile's write-out is
       // complete once every warp has passed this barrier
       for (int i = tid; i < kPWarps * nbp / 2; i += kPThreads) {
         hw32[i] = 0u;
@@ -431,22 +560,23 @@ namespace rgc {
         }
       }
       __syncthreads();
-      // ---- scan: bucket totals (padded to even) -> per-warp cursors and the list
-      // of non-empty buckets ("segments": bucket id + start in the sorted array).
-      // Entries and segments are scanned together, packed 16 + 16 bits.
+      // ---- scan: tile totals per bucket -> first sorted entry of every bucket
+      // (seg_off) and of every (warp, bucket)
+      int tcnt[kPer];
       {
         int sum = 0;
-        for (int i = 0; i < bpt; ++i) {
-          const int b = tid * bpt + i;
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+          const int b   = tid * kPer + i;
+          int       tot = 0;
           if (b < nb) {
-            int tot = 0;
 #pragma unroll
             for (int wq = 0; wq < kPWarps; ++wq) {
               tot += hw16[wq * nbp + b];
             }
-            const int pc = (tot + 1) & ~1;
-            sum += pc + (pc ? 0x10000 : 0);
           }
+          tcnt[i] = tot;
+          sum += tot;
         }
         int incl = sum;
 #pragma unroll
@@ -467,36 +597,24 @@ namespace rgc {
           warp_base += wq < warp ? c : 0;
           total += c;
         }
-        int packed = warp_base + incl - sum;
-        for (int i = 0; i < bpt; ++i) {
-          const int b = tid * bpt + i;
+        int run = warp_base + incl - sum;
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+          const int b = tid * kPer + i;
           if (b < nb) {
-            const int off = packed & 0xffff, k = packed >> 16;
-            int       run = off;
+            seg_off[b] = run;
+            int r2     = run;
 #pragma unroll
             for (int wq = 0; wq < kPWarps; ++wq) {
               const int c        = hw16[wq * nbp + b];
-              hw16[wq * nbp + b] = (unsigned short)run;
-              run += c;
+              hw16[wq * nbp + b] = (unsigned short)r2;
+              r2 += c;
             }
-            if (run != off) {
-              if ((run - off) & 1) {
-                sorted[run] = make_float2(0.0f, 0.0f); // zero-weight pad
-                ++run;
-              }
-              seg_start[k] = off;
-              seg_b[k]     = b;
-              seg_s0[k]    = 0.0f;
-              seg_s1[k]    = 0.0f;
-              packed += (run - off) + 0x10000;
-            }
+            run = r2;
           }
         }
         if (tid == 0) {
-          const int nseg  = total >> 16;
-          seg_start[nseg] = total & 0xffff;
-          seg_b[nseg]     = 0;
-          scan_tmp[kPWarps] = nseg;
+          scan_tmp[2 * kPWarps] = total;
         }
       }
       __syncthreads();
@@ -508,95 +626,126 @@ namespace rgc {
           const int      idx = warp * (kPTile / kPWarps) + step * 32 + lane;
           const unsigned key = stage_k[idx];
           if (key != kInvalidKey) {
-            const unsigned rk = (rank_pack[step >> 1] >> ((step & 1) * 16)) & 0xffffu;
-            sorted[(unsigned)basep[key] + rk] = stage_cw[idx];
+            const unsigned rk  = (rank_pack[step >> 1] >> ((step & 1) * 16)) & 0xffffu;
+            const unsigned pos = (unsigned)basep[key] + rk;
+            sorted[pos]        = stage_cw[idx];
+            sorted_k[pos]      = (unsigned short)key;
           }
         }
       }
       __syncthreads();
-      // staging buffers are free again: fetch the next tile underneath the pair loop
-      if (tid == 0 && tile + gridDim.x < ntiles) {
+      // staging buffers are free again: fetch the next tile underneath the write-out
+      if (tid == 0 && tile + 1 < t1) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue_tile_copy(tile + gridDim.x);
+        issue_tile_copy(tile + 1);
       }
-      // ---- pair phase: the segment list is split between the warp rows by the cost
-      // model  entries + seg_cost * segments;  a row boundary inside a bucket splits
-      // that bucket's segment
+      // ---- write-out: consecutive threads write consecutive sorted entries; a bucket's
+      // run of this tile continues where the row's previous tiles left the bucket
       {
-        const int nseg  = scan_tmp[kPWarps];
-        const int total = seg_start[nseg];
-        const int segc  = P.seg_cost;
-        auto pos_of_cost = [&](int target, int& k_out) -> int {
-          int l = 0, h = max(nseg - 1, 0);
-          while (l < h) { // largest k with cost_before(k) <= target
-            const int mid = (l + h + 1) >> 1;
-            if (seg_start[mid] + segc * mid <= target) {
-              l = mid;
-            } else {
-              h = mid - 1;
-            }
-          }
-          k_out           = l;
-          const int s0    = seg_start[l];
-          const int within = max(0, target - (s0 + segc * l) - segc) & ~1;
-          return min(seg_start[l + 1], s0 + within);
-        };
-        const int ctotal = total + segc * nseg;
-        int       k = 0, kdummy = 0;
-        const int lo = row == 0 ? 0 : pos_of_cost((int)(((long long)ctotal * row) / rows), k);
-        const int hi = row == rows - 1
-                         ? total
-                         : pos_of_cost((int)(((long long)ctotal * (row + 1)) / rows), kdummy);
-        if (lo < hi) {
-          if (seg_start[k + 1] <= lo) {
-            ++k;
-          }
-          const float4* sorted4 = reinterpret_cast<const float4*>(sorted);
-          int           nedges  = 0;
-          // coefficients of the current segment; those of the next one are fetched
-          // before the pair loop runs so their latency hides underneath it
-          int   b_cur = seg_b[k];
-          int   s_beg = seg_start[k], s_end = seg_start[k + 1];
-          float fap[GPW], sgn[GPW], ds[GPW];
+        const int total = scan_tmp[2 * kPWarps];
+        for (int i = tid; i < total; i += kPThreads) {
+          const int k = sorted_k[i];
+          P.sorted[gcur[k] + (i - seg_off[k])] = sorted[i];
+        }
+      }
+      __syncthreads();
 #pragma unroll
-          for (int g = 0; g < GPW; ++g) {
-            const float4 dh = coef[max(aoff[g] + b_cur, 0)];
-            ds[g]  = dh.x;
-            sgn[g] = dh.z;
-            fap[g] = (fa0[g] - dh.y) * dh.z;
-          }
-          for (;;) {
-            const int  pos  = max(s_beg, lo);
-            const int  end  = min(s_end, hi);
-            const bool full = (pos == s_beg) && (end == s_end);
-            const bool more = s_end < hi;
-            // next segment (reads one past the list's end are harmless: k + 2 <= nseg + 1
-            // is guarded by `more`)
-            int    b_nxt = 0, n_beg = 0, n_end = 0;
-            float4 dhn[GPW];
-            if (more) {
-              b_nxt = seg_b[k + 1];
-              n_beg = s_end;
-              n_end = seg_start[k + 2];
+      for (int i = 0; i < kPer; ++i) {
+        const int b = tid * kPer + i;
+        if (b < nb) {
+          gcur[b] += tcnt[i];
+        }
+      }
+    }
+  }
+
+  // ---- kernel 4: the pair loop over the globally bucket-sorted (fc, w)
+  template <int GPW>
+  __global__ void __launch_bounds__(kPThreads, 2)
+    sync_pair_kernel(const __grid_constant__ PairParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4*             coef   = reinterpret_cast<float4*>(smem_raw + P.o_coef);
+    int*                bstart = reinterpret_cast<int*>(smem_raw + P.o_bstart);
+    int*                pstart = reinterpret_cast<int*>(smem_raw + P.o_pstart);
+    int*                tmp    = reinterpret_cast<int*>(smem_raw + P.o_tmp);
+    double*             red    = reinterpret_cast<double*>(smem_raw + P.o_red);
+
+    const int tid  = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int col  = warp % P.ncols;
+    const int nb   = P.nb;
+    float4*             ring = reinterpret_cast<float4*>(smem_raw + P.o_ring) +
+                   warp * (kStages * kStageLen / 2);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + P.o_mbar) +
+                               warp * kStages;
+    if (lane == 0) {
 #pragma unroll
-              for (int g = 0; g < GPW; ++g) {
-                dhn[g] = coef[max(aoff[g] + b_nxt, 0)];
-              }
-            }
-            float s2[GPW];
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&bars[s], 1);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < P.n_pad; i += kPThreads) {
+      coef[i] = P.coef_dh[i];
+    }
+    block_scan_buckets(P.tot, nb, bstart, pstart, tmp); // ends with __syncthreads()
+
+    int    aoff[GPW];
+    float  fa0[GPW];
+    double accd[GPW];
 #pragma unroll
-            for (int g = 0; g < GPW; ++g) {
-              s2[g] = 0.0f;
-            }
-            // Two particles per broadcast LDS.128; the loads of the next two float4
-            // are in flight while the current two are consumed (ping-pong registers,
-            // no moves).  Per particle all hinges first, then all accumulates, so no
-            // FFMA waits on the FFMA.SAT just before it.  Loads past `end` stay inside
-            // the sorted buffer's slack and are never consumed.
-            int       p  = pos >> 1;
-            const int pe = end >> 1;
-            float4    q0 = sorted4[p];
-            float4    q1 = sorted4[p + 1];
+    for (int g = 0; g < GPW; ++g) {
+      const int    slot = (col * GPW + g) * 32 + lane;
+      const int2   si   = P.slot_i[slot];
+      const float2 sf   = P.slot_f[slot];
+      aoff[g] = si.x;
+      fa0[g]  = sf.x;
+      accd[g] = 0.0;
+    }
+
+    const int npieces = pstart[nb];
+    const int wstride = (gridDim.x * kPWarps) / P.ncols;
+    unsigned  tstage  = 0; // stages issued so far by this warp (ring slot and parity)
+
+    for (int piece = (blockIdx.x * kPWarps + warp) / P.ncols; piece < npieces; piece += wstride) {
+      // bucket of the piece: first b with pstart[b + 1] > piece
+      int lo = 0, hi = nb - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pstart[mid + 1] <= piece) {
+          lo = mid + 1;
+        } else {
+          hi = mid;
+        }
+      }
+      const int b    = lo;
+      const int beg  = bstart[b] + (piece - pstart[b]) * kPieceLen;
+      const int end  = min(beg + kPieceLen, bstart[b + 1]);
+      const int nst  = (end - beg + kStageLen - 1) / kStageLen;
+      const float2* src = P.sorted + beg;
+      auto issue = [&](int s) { // stage s of this piece -> ring slot (tstage + s) % kStages
+        const unsigned slot  = (tstage + (unsigned)s) % kStages;
+        const int      cnt   = min(kStageLen, end - beg - s * kStageLen);
+        const unsigned bytes = (unsigned)cnt * sizeof(float2);
+        mbar_expect_tx(&bars[slot], bytes);
+        bulk_g2s(ring + slot * (kStageLen / 2), src + s * kStageLen, bytes, &bars[slot]);
+      };
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < min(nst, kStages); ++s) {
+          issue(s);
+        }
+      }
+      float fap[GPW], sgn[GPW], ds[GPW], s2[GPW];
+#pragma unroll
+      for (int g = 0; g < GPW; ++g) {
+        const float4 dh = coef[max(aoff[g] + b, 0)];
+        ds[g]  = dh.x;
+        sgn[g] = dh.z;
+        fap[g] = (fa0[g] - dh.y) * dh.z;
+        s2[g]  = 0.0f;
+      }
 #define RGC_PAIR_ONE(FC, W)                                                         \
   {                                                                                 \
     float r[GPW];                                                                   \
@@ -604,96 +753,67 @@ namespace rgc {
     _Pragma("unroll") for (int g = 0; g < GPW; ++g) { s2[g] = fmaf((W), r[g], s2[g]); }    \
   }
 #define RGC_PAIR_BODY(Q) RGC_PAIR_ONE((Q).x, (Q).y) RGC_PAIR_ONE((Q).z, (Q).w)
-            for (; p + 4 <= pe; p += 4) {
-              const float4 a0 = sorted4[p + 2];
-              const float4 a1 = sorted4[p + 3];
-              RGC_PAIR_BODY(q0)
-              RGC_PAIR_BODY(q1)
-              q0 = sorted4[p + 4];
-              q1 = sorted4[p + 5];
-              RGC_PAIR_BODY(a0)
-              RGC_PAIR_BODY(a1)
-            }
-            if (p + 2 <= pe) {
-              RGC_PAIR_BODY(q0)
-              RGC_PAIR_BODY(q1)
-              if (p + 2 < pe) {
-                const float4 a0 = sorted4[p + 2];
-                RGC_PAIR_BODY(a0)
-              }
-            } else if (p < pe) {
-              RGC_PAIR_BODY(q0)
-            }
+      for (int s = 0; s < nst; ++s) {
+        const unsigned t    = tstage + (unsigned)s;
+        const unsigned slot = t % kStages;
+        mbar_wait(&bars[slot], (t / kStages) & 1u);
+        const float4* buf = ring + slot * (kStageLen / 2);
+        const int     nq  = min(kStageLen, end - beg - s * kStageLen) >> 1; // float4 = 2 entries
+        if (nq == kStageLen / 2) {
+          // Two particles per broadcast LDS.128; the loads of the next two float4 are in
+          // flight while the current two are consumed (ping-pong registers).  Per particle
+          // all hinges first, then all accumulates, so no FFMA waits on the FFMA.SAT
+          // just before it.
+          float4 q0 = buf[0];
+          float4 q1 = buf[1];
+#pragma unroll 1
+          for (int p = 0; p < kStageLen / 2 - 4; p += 4) {
+            const float4 a0 = buf[p + 2];
+            const float4 a1 = buf[p + 3];
+            RGC_PAIR_BODY(q0)
+            RGC_PAIR_BODY(q1)
+            q0 = buf[p + 4];
+            q1 = buf[p + 5];
+            RGC_PAIR_BODY(a0)
+            RGC_PAIR_BODY(a1)
+          }
+          {
+            const float4 a0 = buf[kStageLen / 2 - 2];
+            const float4 a1 = buf[kStageLen / 2 - 1];
+            RGC_PAIR_BODY(q0)
+            RGC_PAIR_BODY(q1)
+            RGC_PAIR_BODY(a0)
+            RGC_PAIR_BODY(a1)
+          }
+        } else {
+          for (int p = 0; p < nq; ++p) {
+            const float4 q = buf[p];
+            RGC_PAIR_BODY(q)
+          }
+        }
+        __syncwarp();
+        if (lane == 0 && s + kStages < nst) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue(s + kStages);
+        }
+      }
 #undef RGC_PAIR_BODY
 #undef RGC_PAIR_ONE
+      tstage += (unsigned)nst;
 #pragma unroll
-            for (int g = 0; g < GPW; ++g) {
-              acc[g] = fmaf(ds[g], s2[g], acc[g]);
-            }
-            if (col == 0 && lane >= 30) {
-              // spare lanes 30 / 31 of the last group carry S0 / S1 of this segment:
-              // plain stores, folded into the fp64 bucket moments after the barrier
-              const float v = s2[GPW - 1];
-              if (full) {
-                (lane == 30 ? seg_s0 : seg_s1)[k] = v;
-              } else {
-                PairEdge& ed = edge[row * 2 + nedges];
-                ed.b         = b_cur;
-                (lane == 30 ? ed.s0 : ed.s1) = v;
-              }
-            }
-            if (!full) {
-              ++nedges;
-            }
-            if (!more) {
-              break;
-            }
-            ++k;
-            b_cur = b_nxt;
-            s_beg = n_beg;
-            s_end = n_end;
-#pragma unroll
-            for (int g = 0; g < GPW; ++g) {
-              ds[g]  = dhn[g].x;
-              sgn[g] = dhn[g].z;
-              fap[g] = (fa0[g] - dhn[g].y) * dhn[g].z;
-            }
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < GPW; ++g) {
-          accd[g] += (double)acc[g];
-          acc[g] = 0.0f;
-        }
+      for (int g = 0; g < GPW; ++g) {
+        accd[g] = fma((double)ds[g], (double)s2[g], accd[g]);
       }
-      __syncthreads();
-      // ---- fold the segments' moments into the fp64 bucket moments: one thread per
-      // segment; the (at most two per row) pieces of segments cut by a row boundary
-      // are added by the same thread, in row order
-      {
-        const int nseg = scan_tmp[kPWarps];
-        for (int kk = tid; kk < nseg; kk += kPThreads) {
-          const int b  = seg_b[kk];
-          double    a0 = (double)seg_s0[kk], a1 = (double)seg_s1[kk];
-          for (int i = 0; i < rows * 2; ++i) {
-            if (edge[i].b == b) {
-              a0 += (double)edge[i].s0;
-              a1 += (double)edge[i].s1;
-            }
-          }
-          s0tot[b] += a0;
-          s1tot[b] += a1;
-        }
-      }
-      __syncthreads();
-      if (tid < kPWarps * 2) {
-        edge[tid].b = -1;
+      if (col == 0 && lane >= 30) {
+        // spare lanes 30 / 31 of the last group carry S0 / S1 of this piece
+        float* pm = reinterpret_cast<float*>(P.piece_mom + piece);
+        pm[lane - 30] = s2[GPW - 1];
       }
     }
 
-    // ---- CTA reduction over warp rows (fixed order), one partial row per CTA
-    __syncthreads();
-    double* red = reinterpret_cast<double*>(smem_raw + P.o_stage_cw); // 8 * GPW * 32 doubles <= 16 KB
+    // ---- CTA reduction over the warps of a column (fixed order), one partial row per CTA
+    const int rows = kPWarps / P.ncols;
+    const int row  = warp / P.ncols;
 #pragma unroll
     for (int g = 0; g < GPW; ++g) {
       red[(warp * GPW + g) * 32 + lane] = accd[g];
@@ -709,52 +829,69 @@ namespace rgc {
         P.partials[(std::size_t)blockIdx.x * P.nslots + (col * GPW + g) * 32 + lane] = s;
       }
     }
-    for (int i = tid; i < nb; i += kPThreads) {
-      P.moments[(std::size_t)blockIdx.x * 2 * nb + i]      = s0tot[i];
-      P.moments[(std::size_t)blockIdx.x * 2 * nb + nb + i] = s1tot[i];
-    }
   }
 
-  // msum[i] = sum over CTAs (in CTA order) of moments[cta][i], i < 2 * nb
-  __global__ void pair_moments_kernel(const double* __restrict__ moments, int nctas, int n2,
-                                      double* __restrict__ msum) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n2) {
+  // msum[b] = S0 of bucket b, msum[nb + b] = S1: fp64 sums over the bucket's pieces,
+  // lane-strided then a fixed shuffle tree
+  __global__ void __launch_bounds__(kPThreads)
+    pair_moments_kernel(const int* __restrict__ tot, int nb, const float2* __restrict__ piece_mom,
+                        double* __restrict__ msum) {
+    __shared__ int bstart[kPMaxBuckets + 2], pstart[kPMaxBuckets + 2], tmp[2 * kPWarps];
+    block_scan_buckets(tot, nb, bstart, pstart, tmp);
+    const int lane = threadIdx.x & 31;
+    const int b    = blockIdx.x * kPWarps + (threadIdx.x >> 5);
+    if (b >= nb) {
       return;
     }
-    double s = 0.0;
-    for (int c = 0; c < nctas; ++c) {
-      s += moments[(std::size_t)c * n2 + i];
+    double s0 = 0.0, s1 = 0.0;
+    for (int p = pstart[b] + lane; p < pstart[b + 1]; p += 32) {
+      const float2 m = piece_mom[p];
+      s0 += (double)m.x;
+      s1 += (double)m.y;
     }
-    msum[i] = s;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    }
+    if (lane == 0) {
+      msum[b]      = s0;
+      msum[nb + b] = s1;
+    }
   }
 
-  // out[slot] = sum_cta hinge partials + sum_b ( v_q S0_b + s_q (fa S0_b + S1_b) )
-  __global__ void pair_final_kernel(const double* __restrict__ partials, int nctas, int nslots,
-                                    const int2* __restrict__ slot_i,
-                                    const float2* __restrict__ slot_f,
-                                    const double2* __restrict__ coef_vs,
-                                    const double* __restrict__ msum, int nb,
-                                    double* __restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  // out[slot] = sum_cta hinge partials + sum_b ( v_q S0_b + s_q (fa S0_b + S1_b) );
+  // one warp per slot, lane-strided sums and a fixed shuffle tree
+  __global__ void __launch_bounds__(kPThreads)
+    pair_final_kernel(const double* __restrict__ partials, int nctas, int nslots,
+                      const int2* __restrict__ slot_i, const float2* __restrict__ slot_f,
+                      const double2* __restrict__ coef_vs, const double* __restrict__ msum,
+                      int nb, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int j    = blockIdx.x * kPWarps + (threadIdx.x >> 5);
     if (j >= nslots) {
       return;
     }
     double s = 0.0;
-    for (int c = 0; c < nctas; ++c) {
+    for (int c = lane; c < nctas; c += 32) {
       s += partials[(std::size_t)c * nslots + j];
     }
-    const int2   si  = slot_i[j];
-    const double fa  = (double)slot_f[j].x;
-    double       lin = 0.0;
+    const int2   si = slot_i[j];
+    const double fa = (double)slot_f[j].x;
     if (si.x >= 0) {
-      for (int b = 0; b < nb; ++b) {
+      for (int b = lane; b < nb; b += 32) {
         const double2 vs = coef_vs[si.x + b];
         const double  S0 = msum[b], S1 = msum[nb + b];
-        lin += fma(vs.x, S0, vs.y * fma(fa, S0, S1));
+        s += fma(vs.x, S0, vs.y * fma(fa, S0, S1));
       }
     }
-    out[j] = s + lin;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, off);
+    }
+    if (lane == 0) {
+      out[j] = s;
+    }
   }
 
   // ------------------------------------------------------------------ host side
@@ -783,7 +920,7 @@ namespace rgc {
       amax = std::max(amax, a);
     }
     const double spread = amax - amin;
-    return (double)tp.T + std::ceil(spread) + 2.0 <= (double)kPMaxBuckets;
+    return (double)tp.T + std::ceil(spread) + 4.0 <= (double)kPMaxBuckets;
   }
 
   static void make_pair_plan(const TablePlan& tp, const float* bins_e_syn,
@@ -898,28 +1035,46 @@ namespace rgc {
     return fail(RGC_ERR_INVALID, "internal: bad groups per warp %d", gpw);
   }
 
-  // One launch over one chunk of bins.  acc[s] = sum_i w_i F_is for s < bins.size()
-  // (before the e_syn factor), in the caller's chunk order.
+  // One pipeline pass per <= 2^27 particles over one chunk of bins.
+  // acc[s] = sum_i w_i F_is for s < bins.size() (before the e_syn factor), in the
+  // caller's chunk order.
   int run_spectrum_pair(const rgc_particles_t* prtls, std::size_t n, float B0, float g_syn,
                         float e_at, const TablePlan& tp, const float* bins_e_syn,
                         const std::vector<int>& bins, std::vector<double>& acc, float* main_ms) {
     auto&    c = ctx();
     PairPlan pp;
     make_pair_plan(tp, bins_e_syn, bins, pp);
-    const PairSmem    L      = pair_smem_layout(pp.n_pad, pp.nb, pp.nbp);
-    const std::size_t smem   = L.total;
-    const int         per_sm = smem <= 113 * 1024 ? 2 : 1;
-    if (smem > 227 * 1024) {
+    if (pp.nb >= kPMaxBuckets || pp.nbp > kPMaxBuckets) {
+      return fail(RGC_ERR_INVALID, "internal: %d buckets exceed the pair path's limit", pp.nb);
+    }
+    const PairSmem    L    = pair_smem_layout(pp.n_pad, pp.nbp, pp.gpw);
+    const std::size_t smem = L.total;
+    if (smem > 113 * 1024) {
       return fail(RGC_ERR_INVALID, "internal: pair kernel needs %zu B of shared memory", smem);
     }
-    // particles are processed in chunks so the staged (fc, w, key) stay bounded
-    // (10 B per particle); chunk results are summed on the host in chunk order
+    // particles are processed in passes so the staged and sorted (fc, w, key) stay
+    // bounded (18 B per particle); pass results are summed on the host in pass order
     const std::size_t chunk_max = std::size_t(1) << 27;
-    const std::size_t nchunk0   = std::min(n, chunk_max);
-    const std::size_t ntiles0   = (nchunk0 + kPTile - 1) / kPTile;
-    const std::size_t npad0     = ntiles0 * kPTile;
-    const int nctas = (int)std::min<std::size_t>((std::size_t)c.sm_count * per_sm,
-                                                 std::max<std::size_t>(ntiles0, 1));
+    const std::size_t cnt0      = std::min(n, chunk_max);
+    struct Geom {
+      int ntiles, rows, tiles_per_row, ctas1, tiles_per_cta1;
+    };
+    auto geom_for = [&](std::size_t cnt) {
+      Geom g;
+      g.ntiles         = (int)((cnt + kPTile - 1) / kPTile);
+      g.rows           = std::max(1, std::min(c.sm_count * 2, g.ntiles));
+      g.tiles_per_row  = (g.ntiles + g.rows - 1) / g.rows;
+      g.rows           = (g.ntiles + g.tiles_per_row - 1) / g.tiles_per_row;
+      g.ctas1          = std::max(1, std::min(c.sm_count * 3, g.ntiles));
+      g.tiles_per_cta1 = (g.ntiles + g.ctas1 - 1) / g.ctas1;
+      g.ctas1          = (g.ntiles + g.tiles_per_cta1 - 1) / g.tiles_per_cta1;
+      return g;
+    };
+    const Geom        g0    = geom_for(cnt0);
+    const int         rows0 = g0.rows;
+    const std::size_t npad0 = (std::size_t)g0.ntiles * kPTile;
+    const int         pair_ctas   = c.sm_count * 2;
+    const std::size_t max_pieces  = cnt0 / kPieceLen + (std::size_t)pp.nbp + 2;
     auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
     const std::size_t off_si   = 0;
     const std::size_t off_sf   = align(off_si + pp.nslots * sizeof(int2));
@@ -928,10 +1083,13 @@ namespace rgc {
     const std::size_t off_msum = align(off_vs + pp.n_pad * sizeof(double2));
     const std::size_t off_out  = align(off_msum + 2 * pp.nb * sizeof(double));
     const std::size_t off_part = align(off_out + pp.nslots * sizeof(double));
-    const std::size_t off_mom  = align(off_part + (std::size_t)nctas * pp.nslots * sizeof(double));
-    const std::size_t off_cw   = align(off_mom + (std::size_t)nctas * 2 * pp.nb * sizeof(double));
+    const std::size_t off_tot  = align(off_part + (std::size_t)pair_ctas * pp.nslots * sizeof(double));
+    const std::size_t off_cnt  = align(off_tot + (std::size_t)pp.nbp * sizeof(int));
+    const std::size_t off_mom  = align(off_cnt + (std::size_t)pp.nbp * rows0 * sizeof(int));
+    const std::size_t off_cw   = align(off_mom + max_pieces * sizeof(float2));
     const std::size_t off_keys = align(off_cw + npad0 * sizeof(float2));
-    const std::size_t total    = off_keys + npad0 * sizeof(unsigned short);
+    const std::size_t off_sort = align(off_keys + npad0 * sizeof(unsigned short));
+    const std::size_t total    = off_sort + (cnt0 + pp.nbp + 64) * sizeof(float2);
     void*             scratch  = nullptr;
     RGC_TRY(ensure_scratch(total, &scratch));
     char* sb = static_cast<char*>(scratch);
@@ -956,30 +1114,29 @@ namespace rgc {
     P.inv_B0           = 1.0 / (double)B0;
     P.e_scale          = (double)e_at / (double)(g_syn * g_syn);
     P.cells_per_octave = 0.30102999566398119521 / tp.dL;
-    P.c0       = pp.c0;
-    P.inv_dL   = 1.0 / tp.dL;
-    P.c_lo     = pp.c_lo;
-    P.c_hi     = pp.c_hi;
-    P.cw       = reinterpret_cast<float2*>(sb + off_cw);
-    P.keys     = reinterpret_cast<unsigned short*>(sb + off_keys);
-    P.partials = reinterpret_cast<double*>(sb + off_part);
-    P.moments  = reinterpret_cast<double*>(sb + off_mom);
-    P.nslots   = pp.nslots;
-    {
-      const char* sc = std::getenv("RGC_PAIR_SEG_COST"); // tuning knob
-      P.seg_cost     = sc ? std::max(0, std::atoi(sc)) : kSegCostDefault;
-    }
-    P.o_coef = (int)L.coef; P.o_s0tot = (int)L.s0tot; P.o_s1tot = (int)L.s1tot;
-    P.o_start = (int)L.start; P.o_cstart = (int)L.cstart; P.o_hw = (int)L.hw;
-    P.o_stage_cw = (int)L.stage_cw; P.o_stage_k = (int)L.stage_k; P.o_sorted = (int)L.sorted;
-    P.o_edge = (int)L.edge; P.o_scan = (int)L.scan; P.o_mbar = (int)L.mbar;
-    P.o_seg_s0 = (int)L.seg_s0; P.o_seg_s1 = (int)L.seg_s1;
+    P.c0        = pp.c0;
+    P.inv_dL    = 1.0 / tp.dL;
+    P.c_lo      = pp.c_lo;
+    P.c_hi      = pp.c_hi;
+    P.cw        = reinterpret_cast<float2*>(sb + off_cw);
+    P.keys      = reinterpret_cast<unsigned short*>(sb + off_keys);
+    P.counts    = reinterpret_cast<int*>(sb + off_cnt);
+    P.tot       = reinterpret_cast<int*>(sb + off_tot);
+    P.sorted    = reinterpret_cast<float2*>(sb + off_sort);
+    P.piece_mom = reinterpret_cast<float2*>(sb + off_mom);
+    P.partials  = reinterpret_cast<double*>(sb + off_part);
+    P.nslots    = pp.nslots;
+    P.o_coef = (int)L.coef; P.o_bstart = (int)L.bstart; P.o_pstart = (int)L.pstart;
+    P.o_tmp = (int)L.tmp; P.o_ring = (int)L.ring; P.o_mbar = (int)L.mbar; P.o_red = (int)L.red;
     double* d_msum = reinterpret_cast<double*>(sb + off_msum);
     double* d_out  = reinterpret_cast<double*>(sb + off_out);
     std::vector<double> out_host(pp.nslots), out_sum(pp.nslots, 0.0);
-    float               pro_ms = 0.f;
+    float               pro_ms = 0.f, sort_ms = 0.f;
     const char*         pm       = std::getenv("RGC_PROLOGUE_MINB"); // tuning knob
     const int           pro_minb = pm ? std::atoi(pm) : 3;
+    const std::size_t   sort_smem = sort_smem_layout(pp.nbp).total;
+    RGC_CUDA(cudaFuncSetAttribute(sync_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sort_smem));
     for (std::size_t off = 0; off < n; off += chunk_max) {
       const std::size_t cnt = std::min(chunk_max, n - off);
       for (int d = 0; d < 3; ++d) {
@@ -987,45 +1144,56 @@ namespace rgc {
         P.e[d] = prtls->col[RGC_Q_E][d] + off;
         P.b[d] = prtls->col[RGC_Q_B][d] + off;
       }
-      P.nprtl = cnt;
-      P.npad  = ((cnt + kPTile - 1) / kPTile) * kPTile;
-      const int grid1 = (int)std::min<std::size_t>((std::size_t)c.sm_count * 8,
-                                                   (P.npad / 4 + 255) / 256);
-      const int grid2 = (int)std::min<std::size_t>((std::size_t)nctas, P.npad / kPTile);
+      const Geom g     = geom_for(cnt);
+      P.nprtl          = cnt;
+      P.ntiles         = g.ntiles;
+      P.rows           = g.rows;
+      P.tiles_per_row  = g.tiles_per_row;
+      P.tiles_per_cta1 = g.tiles_per_cta1;
       RGC_CUDA(cudaEventRecord(c.ev[2], c.stream));
+      RGC_CUDA(cudaMemsetAsync(P.counts, 0, (std::size_t)pp.nbp * g.rows * sizeof(int), c.stream));
       if (pro_minb == 4) {
-        sync_prologue_kernel<4><<<grid1, 256, 0, c.stream>>>(P);
+        sync_prologue_kernel<4><<<g.ctas1, kPThreads, 0, c.stream>>>(P);
       } else {
-        sync_prologue_kernel<3><<<grid1, 256, 0, c.stream>>>(P);
+        sync_prologue_kernel<3><<<g.ctas1, kPThreads, 0, c.stream>>>(P);
       }
       RGC_CUDA(cudaGetLastError());
       RGC_CUDA(cudaEventRecord(c.ev[3], c.stream));
-      RGC_TRY(launch_pair(pp.gpw, dim3(grid2), smem, c.stream, P));
+      pair_colscan_kernel<<<(pp.nb + kPWarps - 1) / kPWarps, kPThreads, 0, c.stream>>>(
+        P.counts, P.rows, pp.nb, P.tot);
+      RGC_CUDA(cudaGetLastError());
+      sync_sort_kernel<<<g.rows, kPThreads, sort_smem, c.stream>>>(P);
+      RGC_CUDA(cudaGetLastError());
+      RGC_CUDA(cudaEventRecord(c.ev[5], c.stream));
+      RGC_TRY(launch_pair(pp.gpw, dim3(pair_ctas), smem, c.stream, P));
       RGC_CUDA(cudaGetLastError());
       RGC_CUDA(cudaEventRecord(c.ev[4], c.stream));
-      pair_moments_kernel<<<(2 * pp.nb + 127) / 128, 128, 0, c.stream>>>(P.moments, grid2,
-                                                                         2 * pp.nb, d_msum);
+      pair_moments_kernel<<<(pp.nb + kPWarps - 1) / kPWarps, kPThreads, 0, c.stream>>>(
+        P.tot, pp.nb, P.piece_mom, d_msum);
       RGC_CUDA(cudaGetLastError());
-      pair_final_kernel<<<(pp.nslots + 63) / 64, 64, 0, c.stream>>>(
-        P.partials, grid2, pp.nslots, P.slot_i, P.slot_f,
+      pair_final_kernel<<<(pp.nslots + kPWarps - 1) / kPWarps, kPThreads, 0, c.stream>>>(
+        P.partials, pair_ctas, pp.nslots, P.slot_i, P.slot_f,
         reinterpret_cast<const double2*>(sb + off_vs), d_msum, pp.nb, d_out);
       RGC_CUDA(cudaGetLastError());
-      count_launch(4);
+      count_launch(6);
       RGC_CUDA(cudaMemcpyAsync(out_host.data(), d_out, pp.nslots * sizeof(double),
                                cudaMemcpyDeviceToHost, c.stream));
       RGC_CUDA(cudaStreamSynchronize(c.stream));
       float ms = 0.f;
-      RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[3], c.ev[4]));
+      RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[5], c.ev[4]));
       if (main_ms) {
         *main_ms += ms;
       }
       RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]));
       pro_ms += ms;
+      RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[3], c.ev[5]));
+      sort_ms += ms;
       for (int s2 = 0; s2 < pp.nslots; ++s2) {
         out_sum[s2] += out_host[s2];
       }
     }
     c.last_ms[2] = pro_ms;
+    c.last_ms[3] = sort_ms;
     out_host.swap(out_sum);
     // bins[] is in chunk order; slots were filled in the same order
     acc.assign(bins.size(), 0.0);
