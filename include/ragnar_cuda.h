@@ -223,7 +223,7 @@ int rgc_ic_spectrum(const float* g_prtls, const float* f_prtls, size_t nprtls,
  * hot-path call on this thread: [0] total, [1] dominant kernel only. */
 int rgc_last_kernel_ms(float ms[2]);
 /* same, up to n = 4 entries: [2] the per-particle prologue kernel of the spectrum
- * (sync_prologue_kernel), [3] reserved */
+ * (sync_prologue_kernel), [3] its bucket-sort kernels (column scan + sync_sort_kernel) */
 int rgc_last_kernel_times(float* ms, int n);
 
 /* Roofline denominators measured on the device, on the compute stream (bench

@@ -175,7 +175,7 @@ def last_kernel_ms():
 
 
 def last_kernel_times():
-    """(total, dominant kernel, prologue kernel, reserved) of the last hot-path call, ms"""
+    """(total, dominant kernel, prologue kernel, sort kernels) of the last hot-path call, ms"""
     ms = (C.c_float * 4)()
     check(lib().rgc_last_kernel_times(ms, 4))
     return tuple(float(x) for x in ms)

@@ -296,6 +296,77 @@ namespace rgc {
     return u2f(hi);
   }
 
+
+  // Host-side plan of one histogram configuration (reference particles.cpp:231-245
+  // evaluated through rgc_hostmath.cpp): thresholds, per-bin fixed-point scales,
+  // bin-guess coefficients.  A few recent plans are kept.
+  struct HistPlan {
+    std::vector<float>  bins;
+    bool                fv { true }, weighted { true };
+    std::vector<float4> binfo;
+    std::vector<double> inv_scale;
+    int                 est_ok { 0 };
+    float               estA { 0 }, estB { 0 };
+  };
+
+  static const HistPlan& hist_plan(const float* bins, std::size_t n, bool fv, bool weighted,
+                                   float emin, float emax) {
+    static thread_local std::vector<HistPlan> cache;
+    for (const auto& hp : cache) {
+      if (hp.fv == fv && hp.weighted == weighted && hp.bins.size() == n &&
+          std::memcmp(hp.bins.data(), bins, n * sizeof(float)) == 0) {
+        return hp;
+      }
+    }
+    if (cache.size() >= 8) {
+      cache.erase(cache.begin());
+    }
+    cache.emplace_back();
+    HistPlan& hp = cache.back();
+    hp.bins.assign(bins, bins + n);
+    hp.fv       = fv;
+    hp.weighted = weighted;
+    // ---- threshold table
+    std::vector<float> thr(n + 1);
+    thr[0] = 0.0f;
+    for (std::size_t b = 1; b < n; ++b) {
+      thr[b] = threshold_for(b, fv, emin, emax, n);
+    }
+    thr[n] = u2f(0x7f800001u);
+    std::vector<float4>& binfo = hp.binfo;
+    std::vector<double>& inv_scale = hp.inv_scale;
+    binfo.assign(n, make_float4(0.f, 0.f, 0.f, 0.f));
+    inv_scale.assign(n, 0.0);
+    for (std::size_t b = 0; b < n; ++b) {
+      float scale = 0.0f;
+      if (weighted && b > 0 && b + 1 < n && thr[b] == thr[b] && thr[b + 1] == thr[b + 1] &&
+          thr[b + 1] > thr[b]) {
+        // all energies of the bin lie in [E(thr[b]), E(thr[b+1])): weights within
+        // (1/E_hi, 1/E_lo]; fixed point is used when that range is narrow
+        const double e_lo = host_energy_from_usqr(thr[b], fv);
+        const double e_hi = host_energy_from_usqr(thr[b + 1], fv);
+        if (e_lo > 0.0 && std::isfinite(e_hi) && e_hi / e_lo <= 4.0) {
+          const double s = std::ldexp(0.98, kWeightBits) * e_lo; // w_max * s = 0.98 * 2^20
+          if (s > 1e-30 && s < 1e30) {
+            scale        = (float)s;
+            inv_scale[b] = 1.0 / (double)scale;
+          }
+        }
+      }
+      binfo[b] = make_float4(thr[b], thr[b + 1], scale, 0.0f);
+    }
+    // ---- bin guess coefficients: index ~ (n-1) * (0.5*log10(X) - log10(emin)) / log10f(emax/emin)
+    {
+      const double den = (double)std::log10(emax / emin);
+      const double A   = (double)(n - 1) * 0.5 * std::log10(2.0) / den;
+      const double B   = -(double)(n - 1) * std::log10((double)emin) / den;
+      hp.est_ok = (emin > 0.0f && std::isfinite(A) && std::isfinite(B) && den > 0.0) ? 1 : 0;
+      hp.estA   = (float)A;
+      hp.estB   = (float)B;
+    }
+    return hp;
+  }
+
 } // namespace rgc
 
 using namespace rgc;
@@ -327,43 +398,15 @@ extern "C" {
     }
     const bool fv       = fourvel != 0;
     const bool weighted = log_spaced != 0;
-    // ---- threshold table
-    std::vector<float> thr(n + 1);
-    thr[0] = 0.0f;
-    for (std::size_t b = 1; b < n; ++b) {
-      thr[b] = threshold_for(b, fv, emin, emax, n);
-    }
-    thr[n] = u2f(0x7f800001u);
-    std::vector<float4> binfo(n);
-    std::vector<double> inv_scale(n, 0.0);
-    for (std::size_t b = 0; b < n; ++b) {
-      float scale = 0.0f;
-      if (weighted && b > 0 && b + 1 < n && thr[b] == thr[b] && thr[b + 1] == thr[b + 1] &&
-          thr[b + 1] > thr[b]) {
-        // all energies of the bin lie in [E(thr[b]), E(thr[b+1])): weights within
-        // (1/E_hi, 1/E_lo]; fixed point is used when that range is narrow
-        const double e_lo = host_energy_from_usqr(thr[b], fv);
-        const double e_hi = host_energy_from_usqr(thr[b + 1], fv);
-        if (e_lo > 0.0 && std::isfinite(e_hi) && e_hi / e_lo <= 4.0) {
-          const double s = std::ldexp(0.98, kWeightBits) * e_lo; // w_max * s = 0.98 * 2^20
-          if (s > 1e-30 && s < 1e30) {
-            scale        = (float)s;
-            inv_scale[b] = 1.0 / (double)scale;
-          }
-        }
-      }
-      binfo[b] = make_float4(thr[b], thr[b + 1], scale, 0.0f);
-    }
-    // ---- bin guess coefficients: index ~ (n-1) * (0.5*log10(X) - log10(emin)) / log10f(emax/emin)
+    // ---- threshold table, bin info and the bin-guess coefficients depend only on
+    // (bins, fourvel, log_spaced): built once (199 bisections through libm) and kept
+    const HistPlan& plan = hist_plan(bins, n, fv, weighted, emin, emax);
+    const std::vector<float4>& binfo     = plan.binfo;
+    const std::vector<double>& inv_scale = plan.inv_scale;
     HistParams P {};
-    {
-      const double den = (double)std::log10(emax / emin);
-      const double A   = (double)(n - 1) * 0.5 * std::log10(2.0) / den;
-      const double B   = -(double)(n - 1) * std::log10((double)emin) / den;
-      P.est_ok = (emin > 0.0f && std::isfinite(A) && std::isfinite(B) && den > 0.0) ? 1 : 0;
-      P.estA   = (float)A;
-      P.estB   = (float)B;
-    }
+    P.est_ok = plan.est_ok;
+    P.estA   = plan.estA;
+    P.estB   = plan.estB;
     for (int d = 0; d < 3; ++d) {
       P.u[d] = p->col[RGC_Q_U][d];
     }
@@ -435,11 +478,20 @@ extern "C" {
     count_launch(1);
     RGC_CUDA(cudaEventRecord(c.ev[1], c.stream));
 
-    // ---- combine: clamp partials (fixed order) on the host, integer sums exact
-    std::vector<double> clamp((std::size_t)nctas * 2);
-    RGC_CUDA(cudaMemcpyAsync(clamp.data(), P.clamp_part, clamp.size() * sizeof(double),
-                             cudaMemcpyDeviceToHost, c.stream));
-    RGC_CUDA(cudaStreamSynchronize(c.stream));
+    // ---- combine: one D2H of [counts | fixed-point sums | fp64 slow path | clamp
+    // partials]; clamp partials are summed in CTA order on the host, integer sums exact
+    std::vector<unsigned char> raw(total - off_counts);
+    auto fetch = [&]() -> int {
+      RGC_CUDA(cudaMemcpyAsync(raw.data(), sbase + off_counts, raw.size(), cudaMemcpyDeviceToHost,
+                               c.stream));
+      RGC_CUDA(cudaStreamSynchronize(c.stream));
+      return RGC_OK;
+    };
+    RGC_TRY(fetch());
+    const auto* counts = reinterpret_cast<const unsigned long long*>(raw.data());
+    const auto* wfx    = reinterpret_cast<const unsigned long long*>(raw.data() + (off_wfx - off_counts));
+    const auto* wslow  = reinterpret_cast<const double*>(raw.data() + (off_wslow - off_counts));
+    const auto* clamp  = reinterpret_cast<const double*>(raw.data() + (off_clamp - off_counts));
     double clamp_sum[2] = { 0.0, 0.0 };
     for (int b = 0; b < nctas; ++b) {
       clamp_sum[0] += clamp[(std::size_t)b * 2 + 0];
@@ -447,9 +499,7 @@ extern "C" {
     }
     if (c.nccl_comm && c.nranks > 1) {
       // fold the clamp sums into the fp64 slow-path array so one all-reduce carries them
-      std::vector<double> slow(n);
-      RGC_CUDA(cudaMemcpyAsync(slow.data(), P.wslow, n * 8, cudaMemcpyDeviceToHost, c.stream));
-      RGC_CUDA(cudaStreamSynchronize(c.stream));
+      std::vector<double> slow(wslow, wslow + n);
       slow[0] += clamp_sum[0];
       if (n > 1) {
         slow[n - 1] += clamp_sum[1];
@@ -463,13 +513,8 @@ extern "C" {
       // reduce them separately
       RGC_TRY(allreduce_sum_u64(P.counts, n));
       RGC_TRY(allreduce_sum_u64(P.wfx, n));
+      RGC_TRY(fetch());
     }
-    std::vector<unsigned long long> counts(n), wfx(n);
-    std::vector<double>             wslow(n);
-    RGC_CUDA(cudaMemcpyAsync(counts.data(), P.counts, n * 8, cudaMemcpyDeviceToHost, c.stream));
-    RGC_CUDA(cudaMemcpyAsync(wfx.data(), P.wfx, n * 8, cudaMemcpyDeviceToHost, c.stream));
-    RGC_CUDA(cudaMemcpyAsync(wslow.data(), P.wslow, n * 8, cudaMemcpyDeviceToHost, c.stream));
-    RGC_CUDA(cudaStreamSynchronize(c.stream));
     float ms = 0.f;
     RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]));
     c.last_ms[0] = ms;
