@@ -449,7 +449,7 @@ namespace rgc {
     L.tmp = o;      o = pair_align16(o + (std::size_t)(2 * kPWarps + 2) * sizeof(int));
     L.gcur = o;     o = pair_align16(o + (std::size_t)nbp * sizeof(int));
     L.seg_off = o;  o = pair_align16(o + (std::size_t)(nbp + 2) * sizeof(int));
-    L.hw = o;       o = pair_align16(o + (std::size_t)kPWarps * nbp * sizeof(unsigned short));
+    L.hw = o;       o = pair_align16(o + (std::size_t)kPWarps * nbp * sizeof(int));
     o = (o + 127) & ~std::size_t(127);
     L.stage_cw = o; o = pair_align16(o + (std::size_t)kPTile * sizeof(float2));
     L.stage_k = o;  o = pair_align16(o + (std::size_t)kPTile * sizeof(unsigned short));
@@ -462,6 +462,14 @@ namespace rgc {
 
   // ---- kernel 3: bucket sort of every tile inside shared memory, coalesced write-out
   // of the tile's bucket runs into the global bucket order.  One CTA per row.
+  // ATOMIC_RANK: a particle's rank among its warp's particles of the same bucket is
+  // the return value of one shared-memory atomic on the warp-private cursor (lanes of
+  // one instruction that hit the same cursor are replayed by the hardware in a fixed
+  // order, so the result is reproducible in practice — tests/test_gpu_parity.py
+  // test_repeatable checks it on the device); otherwise 11 ballots per step group the
+  // lanes by key and the group's first lane advances the cursor (order guaranteed by
+  // construction; RGC_SORT_RANK=ballot selects it).
+  template <bool ATOMIC_RANK>
   __global__ void __launch_bounds__(kPThreads, 2)
     sync_sort_kernel(const __grid_constant__ PairParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -471,8 +479,7 @@ namespace rgc {
     int*            scan_tmp = reinterpret_cast<int*>(smem_raw + L.tmp);
     int*            gcur     = reinterpret_cast<int*>(smem_raw + L.gcur);
     int*            seg_off  = reinterpret_cast<int*>(smem_raw + L.seg_off);
-    unsigned short* hw16     = reinterpret_cast<unsigned short*>(smem_raw + L.hw);
-    unsigned*       hw32     = reinterpret_cast<unsigned*>(smem_raw + L.hw);
+    int*            hw       = reinterpret_cast<int*>(smem_raw + L.hw);
     float2*         stage_cw = reinterpret_cast<float2*>(smem_raw + L.stage_cw);
     unsigned short* stage_k  = reinterpret_cast<unsigned short*>(smem_raw + L.stage_k);
     float2*         sorted   = reinterpret_cast<float2*>(smem_raw + L.sorted);
@@ -518,45 +525,61 @@ namespace rgc {
     constexpr int kPer = kPMaxBuckets / kPThreads; // buckets per thread in the scan
     unsigned      parity = 0;
     for (int tile = t0; tile < t1; ++tile) {
-      // ---- per-warp bucket cursors (u16), zeroed; the previous tile's write-out is
+      // ---- per-warp bucket cursors, zeroed; the previous tile's write-out is
       // complete once every warp has passed this barrier
-      for (int i = tid; i < kPWarps * nbp / 2; i += kPThreads) {
-        hw32[i] = 0u;
+      for (int i = tid; i < kPWarps * nbp; i += kPThreads) {
+        hw[i] = 0;
       }
       __syncthreads();
       mbar_wait(mbar, parity);
       parity ^= 1u;
-      // ---- pass A: stable rank of every particle among its warp's particles of the
-      // same bucket (warp w owns tile entries [512 w, 512 w + 512), 32 per step).
-      // The lanes of a step are grouped by key (match_key11); the group's first lane
-      // advances the warp's cursor of that bucket.
-      unsigned short* cur = hw16 + warp * nbp;
-      unsigned        rank_pack[kPSteps / 2]; // u16 ranks, two per register
+      // ---- pass A: rank of every particle among its warp's particles of the same
+      // bucket (warp w owns tile entries [512 w, 512 w + 512), 32 per step)
+      int*     cur = hw + warp * nbp;
+      unsigned rank_pack[kPSteps / 2]; // u16 ranks, two per register
+      if (ATOMIC_RANK) {
 #pragma unroll
-      for (int s4 = 0; s4 < kPSteps; s4 += 4) {
-        unsigned key[4], m[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          key[j] = stage_k[warp * (kPTile / kPWarps) + (s4 + j) * 32 + lane];
-          m[j]   = match_key11(key[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool valid = key[j] != kInvalidKey;
-          const int  lead  = __ffs(m[j]) - 1;
-          int        basev = 0;
-          if (valid && lane == lead) {
-            basev       = cur[key[j]];
-            cur[key[j]] = (unsigned short)(basev + __popc(m[j]));
+        for (int st = 0; st < kPSteps; ++st) {
+          const unsigned key = stage_k[warp * (kPTile / kPWarps) + st * 32 + lane];
+          unsigned       rk  = 0;
+          if (key != kInvalidKey) {
+            rk = (unsigned)atomicAdd(&cur[key], 1);
           }
-          basev = __shfl_sync(0xffffffffu, basev, lead);
-          const unsigned rk = (unsigned)(basev + __popc(m[j] & ((1u << lane) - 1u)));
-          if (((s4 + j) & 1) == 0) {
-            rank_pack[(s4 + j) >> 1] = rk;
+          if ((st & 1) == 0) {
+            rank_pack[st >> 1] = rk;
           } else {
-            rank_pack[(s4 + j) >> 1] |= rk << 16;
+            rank_pack[st >> 1] |= rk << 16;
           }
-          __syncwarp();
+        }
+      } else {
+        // The lanes of a step are grouped by key (match_key11); the group's first lane
+        // advances the warp's cursor of that bucket.
+#pragma unroll
+        for (int s4 = 0; s4 < kPSteps; s4 += 4) {
+          unsigned key[4], m[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            key[j] = stage_k[warp * (kPTile / kPWarps) + (s4 + j) * 32 + lane];
+            m[j]   = match_key11(key[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool valid = key[j] != kInvalidKey;
+            const int  lead  = __ffs(m[j]) - 1;
+            int        basev = 0;
+            if (valid && lane == lead) {
+              basev       = cur[key[j]];
+              cur[key[j]] = basev + __popc(m[j]);
+            }
+            basev = __shfl_sync(0xffffffffu, basev, lead);
+            const unsigned rk = (unsigned)(basev + __popc(m[j] & ((1u << lane) - 1u)));
+            if (((s4 + j) & 1) == 0) {
+              rank_pack[(s4 + j) >> 1] = rk;
+            } else {
+              rank_pack[(s4 + j) >> 1] |= rk << 16;
+            }
+            __syncwarp();
+          }
         }
       }
       __syncthreads();
@@ -572,7 +595,7 @@ namespace rgc {
           if (b < nb) {
 #pragma unroll
             for (int wq = 0; wq < kPWarps; ++wq) {
-              tot += hw16[wq * nbp + b];
+              tot += hw[wq * nbp + b];
             }
           }
           tcnt[i] = tot;
@@ -606,8 +629,8 @@ namespace rgc {
             int r2     = run;
 #pragma unroll
             for (int wq = 0; wq < kPWarps; ++wq) {
-              const int c        = hw16[wq * nbp + b];
-              hw16[wq * nbp + b] = (unsigned short)r2;
+              const int c      = hw[wq * nbp + b];
+              hw[wq * nbp + b] = r2;
               r2 += c;
             }
             run = r2;
@@ -620,7 +643,7 @@ namespace rgc {
       __syncthreads();
       // ---- pass B: scatter to bucket order (cursor base of (warp, bucket) + rank)
       {
-        const unsigned short* basep = hw16 + warp * nbp;
+        const int* basep = hw + warp * nbp;
 #pragma unroll
         for (int step = 0; step < kPSteps; ++step) {
           const int      idx = warp * (kPTile / kPWarps) + step * 32 + lane;
@@ -1056,13 +1079,16 @@ namespace rgc {
     // bounded (18 B per particle); pass results are summed on the host in pass order
     const std::size_t chunk_max = std::size_t(1) << 27;
     const std::size_t cnt0      = std::min(n, chunk_max);
+    const char* sr          = std::getenv("RGC_SORT_RANK"); // "ballot": guaranteed-order ranking
+    const bool  atomic_rank = !(sr && std::strcmp(sr, "ballot") == 0);
+    const int sort_ctas_per_sm = 2;
     struct Geom {
       int ntiles, rows, tiles_per_row, ctas1, tiles_per_cta1;
     };
     auto geom_for = [&](std::size_t cnt) {
       Geom g;
       g.ntiles         = (int)((cnt + kPTile - 1) / kPTile);
-      g.rows           = std::max(1, std::min(c.sm_count * 2, g.ntiles));
+      g.rows           = std::max(1, std::min(c.sm_count * sort_ctas_per_sm, g.ntiles));
       g.tiles_per_row  = (g.ntiles + g.rows - 1) / g.rows;
       g.rows           = (g.ntiles + g.tiles_per_row - 1) / g.tiles_per_row;
       g.ctas1          = std::max(1, std::min(c.sm_count * 3, g.ntiles));
@@ -1135,8 +1161,10 @@ namespace rgc {
     const char*         pm       = std::getenv("RGC_PROLOGUE_MINB"); // tuning knob
     const int           pro_minb = pm ? std::atoi(pm) : 3;
     const std::size_t   sort_smem = sort_smem_layout(pp.nbp).total;
-    RGC_CUDA(cudaFuncSetAttribute(sync_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sort_smem));
+    RGC_CUDA(cudaFuncSetAttribute(sync_sort_kernel<true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    RGC_CUDA(cudaFuncSetAttribute(sync_sort_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
     for (std::size_t off = 0; off < n; off += chunk_max) {
       const std::size_t cnt = std::min(chunk_max, n - off);
       for (int d = 0; d < 3; ++d) {
@@ -1162,7 +1190,11 @@ namespace rgc {
       pair_colscan_kernel<<<(pp.nb + kPWarps - 1) / kPWarps, kPThreads, 0, c.stream>>>(
         P.counts, P.rows, pp.nb, P.tot);
       RGC_CUDA(cudaGetLastError());
-      sync_sort_kernel<<<g.rows, kPThreads, sort_smem, c.stream>>>(P);
+      if (atomic_rank) {
+        sync_sort_kernel<true><<<g.rows, kPThreads, sort_smem, c.stream>>>(P);
+      } else {
+        sync_sort_kernel<false><<<g.rows, kPThreads, sort_smem, c.stream>>>(P);
+      }
       RGC_CUDA(cudaGetLastError());
       RGC_CUDA(cudaEventRecord(c.ev[5], c.stream));
       RGC_TRY(launch_pair(pp.gpw, dim3(pair_ctas), smem, c.stream, P));
