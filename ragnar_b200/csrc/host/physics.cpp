@@ -72,7 +72,7 @@ namespace rgb {
       throw std::runtime_error("bins_e_syn must be in units of mc^2");
     }
     std::vector<real_t> spec(nbins, 0.0f);
-    if (prtls.is_allocated() && prtls.nactive() > 0) {
+    if (prtls.is_allocated()) { // nactive == 0 still joins a multi-rank all-reduce
       check(rgc_sync_spectrum_particles(prtls.handle(), prtls.nactive(), bins_e_syn.host_data(),
                                         nbins, tab.x.data(), tab.y.data(), tab.x.size(), B0,
                                         g_syn, e_syn_at_g_syn, spec.data(), nullptr));

@@ -266,6 +266,27 @@ namespace rgc {
     }
   }
 
+  // wslow[0] += sum_cta clamp[cta][0], wslow[n-1] += sum_cta clamp[cta][1]: lane-strided
+  // partial sums and a fixed shuffle tree (one warp)
+  __global__ void hist_fold_clamp_kernel(const double* __restrict__ clamp, int nctas,
+                                         double* __restrict__ wslow, int n) {
+    const int lane = threadIdx.x;
+    double    s0 = 0.0, s1 = 0.0;
+    for (int b = lane; b < nctas; b += 32) {
+      s0 += clamp[(std::size_t)b * 2 + 0];
+      s1 += clamp[(std::size_t)b * 2 + 1];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    }
+    if (lane == 0) {
+      wslow[0] += s0;
+      wslow[n - 1] += s1;
+    }
+  }
+
   // ------------------------------------------------------------------ host side
   static float u2f(std::uint32_t u) {
     float f;
@@ -456,7 +477,7 @@ extern "C" {
 
     const std::size_t off_binfo  = 0;
     const std::size_t off_counts = align(off_binfo + n * sizeof(float4));
-    const std::size_t off_wfx    = align(off_counts + n * 8);
+    const std::size_t off_wfx    = off_counts + n * 8; // adjacent: one u64 all-reduce of 2n
     const std::size_t off_wslow  = align(off_wfx + n * 8);
     const std::size_t off_clamp  = align(off_wslow + n * 8);
     const std::size_t total      = off_clamp + (std::size_t)nctas * 2 * sizeof(double);
@@ -478,43 +499,26 @@ extern "C" {
     count_launch(1);
     RGC_CUDA(cudaEventRecord(c.ev[1], c.stream));
 
-    // ---- combine: one D2H of [counts | fixed-point sums | fp64 slow path | clamp
-    // partials]; clamp partials are summed in CTA order on the host, integer sums exact
-    std::vector<unsigned char> raw(total - off_counts);
-    auto fetch = [&]() -> int {
-      RGC_CUDA(cudaMemcpyAsync(raw.data(), sbase + off_counts, raw.size(), cudaMemcpyDeviceToHost,
-                               c.stream));
-      RGC_CUDA(cudaStreamSynchronize(c.stream));
-      return RGC_OK;
-    };
-    RGC_TRY(fetch());
+    // ---- combine on the device: the clamp bins' per-CTA partial sums are folded (fixed
+    // order) into the fp64 slow-path array; with a communicator, one fused group of two
+    // all-reduces (u64 counts + fixed-point sums, f64 slow path); then ONE D2H of
+    // [counts | fixed-point sums | fp64 slow path].  Integer sums are exact.
+    hist_fold_clamp_kernel<<<1, 32, 0, c.stream>>>(P.clamp_part, nctas, P.wslow, (int)n);
+    RGC_CUDA(cudaGetLastError());
+    count_launch(1);
+    if (c.nccl_comm && c.nranks > 1) {
+      RGC_TRY(allreduce_group_begin());
+      RGC_TRY(allreduce_sum_u64(P.counts, 2 * n));
+      RGC_TRY(allreduce_sum_f64(P.wslow, n));
+      RGC_TRY(allreduce_group_end());
+    }
+    std::vector<unsigned char> raw(off_clamp - off_counts);
+    RGC_CUDA(cudaMemcpyAsync(raw.data(), sbase + off_counts, raw.size(), cudaMemcpyDeviceToHost,
+                             c.stream));
+    RGC_CUDA(cudaStreamSynchronize(c.stream));
     const auto* counts = reinterpret_cast<const unsigned long long*>(raw.data());
     const auto* wfx    = reinterpret_cast<const unsigned long long*>(raw.data() + (off_wfx - off_counts));
     const auto* wslow  = reinterpret_cast<const double*>(raw.data() + (off_wslow - off_counts));
-    const auto* clamp  = reinterpret_cast<const double*>(raw.data() + (off_clamp - off_counts));
-    double clamp_sum[2] = { 0.0, 0.0 };
-    for (int b = 0; b < nctas; ++b) {
-      clamp_sum[0] += clamp[(std::size_t)b * 2 + 0];
-      clamp_sum[1] += clamp[(std::size_t)b * 2 + 1];
-    }
-    if (c.nccl_comm && c.nranks > 1) {
-      // fold the clamp sums into the fp64 slow-path array so one all-reduce carries them
-      std::vector<double> slow(wslow, wslow + n);
-      slow[0] += clamp_sum[0];
-      if (n > 1) {
-        slow[n - 1] += clamp_sum[1];
-      } else {
-        slow[0] += clamp_sum[1];
-      }
-      clamp_sum[0] = clamp_sum[1] = 0.0;
-      RGC_CUDA(cudaMemcpyAsync(P.wslow, slow.data(), n * 8, cudaMemcpyHostToDevice, c.stream));
-      RGC_TRY(allreduce_sum_f64(P.wslow, n));
-      // counts and fixed-point sums are adjacent u64 arrays only if n*8 is 256-aligned;
-      // reduce them separately
-      RGC_TRY(allreduce_sum_u64(P.counts, n));
-      RGC_TRY(allreduce_sum_u64(P.wfx, n));
-      RGC_TRY(fetch());
-    }
     float ms = 0.f;
     RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]));
     c.last_ms[0] = ms;
@@ -524,12 +528,6 @@ extern "C" {
       double sum;
       if (weighted) {
         sum = (double)wfx[b] * inv_scale[b] + wslow[b];
-        if (b == 0) {
-          sum += clamp_sum[0];
-        }
-        if (b == n - 1) {
-          sum += clamp_sum[1];
-        }
       } else {
         sum = (double)counts[b];
       }

@@ -73,16 +73,23 @@ namespace rgc {
     // reusable device scratch (grown on demand, freed in rgc_finalize)
     void*       scratch { nullptr };
     std::size_t scratch_bytes { 0 };
+    // small device buffer for per-call result vectors (survives scratch re-layouts)
+    void*       result { nullptr };
+    std::size_t result_bytes { 0 };
     std::atomic<std::uint64_t> launches { 0 };
   };
 
   Context& ctx();
   int      ensure_scratch(std::size_t bytes, void** out);
+  int      ensure_result(std::size_t bytes, void** out);
   inline void count_launch(int n = 1) { ctx().launches.fetch_add((std::uint64_t)n); }
 
   // all-reduce (sum) in place on the compute stream; no-op without a communicator
   int allreduce_sum_f64(double* dev, std::size_t n);
   int allreduce_sum_u64(unsigned long long* dev, std::size_t n);
+  // ncclGroupStart / ncclGroupEnd around several all-reduces: one fused launch
+  int allreduce_group_begin();
+  int allreduce_group_end();
 
   // frees the pinned I/O lanes of the HDF5 streaming reader (rgc_tristan.cpp)
   void io_release_lanes();
@@ -124,9 +131,15 @@ namespace rgc {
   // bucketed hinge path (rgc_sync_pair.cu)
   bool pair_path_eligible(const TablePlan& tp, const float* bins_e_syn,
                           const std::vector<int>& bins);
+  // adds the chunk's per-bin sums into d_acc[bins[s]] on the device (stream-ordered)
   int  run_spectrum_pair(const rgc_particles* prtls, std::size_t n, float B0, float g_syn,
                          float e_at, const TablePlan& tp, const float* bins_e_syn,
-                         const std::vector<int>& bins, std::vector<double>& acc, float* main_ms);
+                         const std::vector<int>& bins, double* d_acc, float* main_ms,
+                         bool defer_sync);
+  // after the caller's own stream synchronisation: kernel times of a deferred pass
+  int  collect_pair_times(float* main_ms);
+  // d_acc[binmap[s]] += src[s] for every slot with binmap[s] >= 0
+  int  launch_scatter_add(const double* src, const int* binmap, int nslots, double* d_acc);
 } // namespace rgc
 
 // ------------------------------------------------------------ opaque handles

@@ -12,6 +12,8 @@
 #include "rgc_internal.hpp"
 
 #include <dlfcn.h>
+#include <execinfo.h>
+#include <csignal>
 #include <nccl.h> // types and enum values only; the library is dlopen'ed
 
 #include <cstdlib>
@@ -55,6 +57,23 @@ namespace rgc {
       c.scratch_bytes = want;
     }
     *out = c.scratch;
+    return RGC_OK;
+  }
+
+  int ensure_result(std::size_t bytes, void** out) {
+    auto& c = ctx();
+    if (bytes > c.result_bytes) {
+      if (c.result) {
+        RGC_CUDA(cudaStreamSynchronize(c.stream));
+        RGC_CUDA(cudaFree(c.result));
+        c.result       = nullptr;
+        c.result_bytes = 0;
+      }
+      const std::size_t want = (bytes + 65535) & ~std::size_t(65535);
+      RGC_CUDA(cudaMalloc(&c.result, want));
+      c.result_bytes = want;
+    }
+    *out = c.result;
     return RGC_OK;
   }
 
@@ -116,6 +135,8 @@ namespace rgc {
     ncclResult_t (*CommDestroy)(ncclComm_t) { nullptr };
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t,
                               ncclComm_t, cudaStream_t) { nullptr };
+    ncclResult_t (*GroupStart)() { nullptr };
+    ncclResult_t (*GroupEnd)() { nullptr };
     const char* (*GetErrorString)(ncclResult_t) { nullptr };
   };
 
@@ -149,6 +170,8 @@ namespace rgc {
     RGC_NCCL_SYM(CommInitRank, "ncclCommInitRank");
     RGC_NCCL_SYM(CommDestroy, "ncclCommDestroy");
     RGC_NCCL_SYM(AllReduce, "ncclAllReduce");
+    RGC_NCCL_SYM(GroupStart, "ncclGroupStart");
+    RGC_NCCL_SYM(GroupEnd, "ncclGroupEnd");
     RGC_NCCL_SYM(GetErrorString, "ncclGetErrorString");
 #undef RGC_NCCL_SYM
     return RGC_OK;
@@ -183,6 +206,24 @@ namespace rgc {
     return RGC_OK;
   }
 
+  int allreduce_group_begin() {
+    auto& c = ctx();
+    if (!c.nccl_comm || c.nranks <= 1) {
+      return RGC_OK;
+    }
+    RGC_NCCL(nccl().GroupStart());
+    return RGC_OK;
+  }
+
+  int allreduce_group_end() {
+    auto& c = ctx();
+    if (!c.nccl_comm || c.nranks <= 1) {
+      return RGC_OK;
+    }
+    RGC_NCCL(nccl().GroupEnd());
+    return RGC_OK;
+  }
+
 } // namespace rgc
 
 using namespace rgc;
@@ -211,6 +252,17 @@ extern "C" {
     auto& c = ctx();
     if (c.initialized) {
       return RGC_OK;
+    }
+    if (std::getenv("RGC_DEBUG_SIGNALS")) { // native backtrace on SIGFPE / SIGSEGV (debug aid)
+      auto handler = +[](int sig) {
+        void* frames[64];
+        const int nf = backtrace(frames, 64);
+        backtrace_symbols_fd(frames, nf, 2);
+        signal(sig, SIG_DFL);
+        raise(sig);
+      };
+      signal(SIGFPE, handler);
+      signal(SIGSEGV, handler);
     }
     int ndev = 0;
     rgc_device_count(&ndev);
@@ -268,6 +320,11 @@ extern "C" {
       cudaFree(c.scratch);
       c.scratch       = nullptr;
       c.scratch_bytes = 0;
+    }
+    if (c.result) {
+      cudaFree(c.result);
+      c.result       = nullptr;
+      c.result_bytes = 0;
     }
     for (auto& e : c.ev) {
       if (e) {

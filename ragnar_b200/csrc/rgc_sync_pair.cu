@@ -1059,11 +1059,11 @@ namespace rgc {
   }
 
   // One pipeline pass per <= 2^27 particles over one chunk of bins.
-  // acc[s] = sum_i w_i F_is for s < bins.size() (before the e_syn factor), in the
-  // caller's chunk order.
+  // d_acc[bins[s]] += sum_i w_i F_is (before the e_syn factor), on the device.
   int run_spectrum_pair(const rgc_particles_t* prtls, std::size_t n, float B0, float g_syn,
                         float e_at, const TablePlan& tp, const float* bins_e_syn,
-                        const std::vector<int>& bins, std::vector<double>& acc, float* main_ms) {
+                        const std::vector<int>& bins, double* d_acc, float* main_ms,
+                        bool defer_sync) {
     auto&    c = ctx();
     PairPlan pp;
     make_pair_plan(tp, bins_e_syn, bins, pp);
@@ -1102,7 +1102,8 @@ namespace rgc {
     const int         pair_ctas   = c.sm_count * 2;
     const std::size_t max_pieces  = cnt0 / kPieceLen + (std::size_t)pp.nbp + 2;
     auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
-    const std::size_t off_si   = 0;
+    const std::size_t off_map  = 0;
+    const std::size_t off_si   = align(off_map + pp.nslots * sizeof(int));
     const std::size_t off_sf   = align(off_si + pp.nslots * sizeof(int2));
     const std::size_t off_dh   = align(off_sf + pp.nslots * sizeof(float2));
     const std::size_t off_vs   = align(off_dh + pp.n_pad * sizeof(float4));
@@ -1119,6 +1120,8 @@ namespace rgc {
     void*             scratch  = nullptr;
     RGC_TRY(ensure_scratch(total, &scratch));
     char* sb = static_cast<char*>(scratch);
+    RGC_CUDA(cudaMemcpyAsync(sb + off_map, pp.bin_of_slot.data(), pp.nslots * sizeof(int),
+                             cudaMemcpyHostToDevice, c.stream));
     RGC_CUDA(cudaMemcpyAsync(sb + off_si, pp.slot_i.data(), pp.nslots * sizeof(int2),
                              cudaMemcpyHostToDevice, c.stream));
     RGC_CUDA(cudaMemcpyAsync(sb + off_sf, pp.slot_f.data(), pp.nslots * sizeof(float2),
@@ -1156,7 +1159,6 @@ namespace rgc {
     P.o_tmp = (int)L.tmp; P.o_ring = (int)L.ring; P.o_mbar = (int)L.mbar; P.o_red = (int)L.red;
     double* d_msum = reinterpret_cast<double*>(sb + off_msum);
     double* d_out  = reinterpret_cast<double*>(sb + off_out);
-    std::vector<double> out_host(pp.nslots), out_sum(pp.nslots, 0.0);
     float               pro_ms = 0.f, sort_ms = 0.f;
     const char*         pm       = std::getenv("RGC_PROLOGUE_MINB"); // tuning knob
     const int           pro_minb = pm ? std::atoi(pm) : 3;
@@ -1208,8 +1210,14 @@ namespace rgc {
         reinterpret_cast<const double2*>(sb + off_vs), d_msum, pp.nb, d_out);
       RGC_CUDA(cudaGetLastError());
       count_launch(6);
-      RGC_CUDA(cudaMemcpyAsync(out_host.data(), d_out, pp.nslots * sizeof(double),
-                               cudaMemcpyDeviceToHost, c.stream));
+      RGC_TRY(launch_scatter_add(d_out, reinterpret_cast<const int*>(sb + off_map), pp.nslots,
+                                 d_acc));
+      if (defer_sync && n <= chunk_max) {
+        // single pass: the caller synchronises once and then collects the times
+        c.last_ms[2] = c.last_ms[3] = 0.f;
+        return RGC_OK;
+      }
+      // the events (and the staged arrays) are reused by the next pass: wait here
       RGC_CUDA(cudaStreamSynchronize(c.stream));
       float ms = 0.f;
       RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[5], c.ev[4]));
@@ -1220,20 +1228,21 @@ namespace rgc {
       pro_ms += ms;
       RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[3], c.ev[5]));
       sort_ms += ms;
-      for (int s2 = 0; s2 < pp.nslots; ++s2) {
-        out_sum[s2] += out_host[s2];
-      }
     }
     c.last_ms[2] = pro_ms;
     c.last_ms[3] = sort_ms;
-    out_host.swap(out_sum);
-    // bins[] is in chunk order; slots were filled in the same order
-    acc.assign(bins.size(), 0.0);
-    const int cap = pp.gpw * 32 - 2;
-    for (std::size_t s = 0; s < bins.size(); ++s) {
-      const int cidx = (int)s / cap, r = (int)s % cap;
-      acc[s]         = out_host[(std::size_t)cidx * pp.gpw * 32 + r];
+    return RGC_OK;
+  }
+
+  int collect_pair_times(float* main_ms) {
+    auto& c  = ctx();
+    float ms = 0.f;
+    RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[5], c.ev[4]));
+    if (main_ms) {
+      *main_ms += ms;
     }
+    RGC_CUDA(cudaEventElapsedTime(&c.last_ms[2], c.ev[2], c.ev[3]));
+    RGC_CUDA(cudaEventElapsedTime(&c.last_ms[3], c.ev[3], c.ev[5]));
     return RGC_OK;
   }
 

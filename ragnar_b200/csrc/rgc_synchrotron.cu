@@ -293,6 +293,27 @@ namespace rgc {
     out[j] = s;
   }
 
+  // d_acc[binmap[s]] += src[s]: folds one launch's slot sums into the per-bin result
+  // on the device (launches of one call are stream-ordered; a bin belongs to exactly
+  // one slot of one bin chunk, so there is no concurrent update)
+  __global__ void scatter_add_kernel(const double* __restrict__ src, const int* __restrict__ binmap,
+                                     int nslots, double* __restrict__ d_acc) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nslots) {
+      const int b = binmap[s];
+      if (b >= 0) {
+        d_acc[b] += src[s];
+      }
+    }
+  }
+
+  int launch_scatter_add(const double* src, const int* binmap, int nslots, double* d_acc) {
+    scatter_add_kernel<<<(nslots + 127) / 128, 128, 0, ctx().stream>>>(src, binmap, nslots, d_acc);
+    RGC_CUDA(cudaGetLastError());
+    count_launch(1);
+    return RGC_OK;
+  }
+
   // ------------------------------------------------------------------ host side
   static int make_table_plan(const float* tab_x, const float* tab_y, std::size_t T,
                              TablePlan& tp) {
@@ -472,22 +493,34 @@ namespace rgc {
     chunk_bins(tp, bins_e_syn, nbins, chunks, nan_bins);
 
     acc_host.assign(nbins, 0.0);
+    // per-bin sums are accumulated on the device (one small buffer that survives the
+    // scratch re-layouts of the launches), all-reduced once and read back once
+    void* result = nullptr;
+    RGC_TRY(ensure_result(nbins * sizeof(double), &result));
+    double* d_acc = static_cast<double*>(result);
     RGC_CUDA(cudaEventRecord(c.ev[0], c.stream));
-    float main_ms = 0.f;
+    RGC_CUDA(cudaMemsetAsync(d_acc, 0, nbins * sizeof(double), c.stream));
+    float main_ms  = 0.f;
+    bool  deferred = false;
     // ---- bucketed hinge path (rgc_sync_pair.cu) for every chunk it can take;
     // RGC_SPECTRUM_PATH=gather forces the gather kernel below (A/B checks)
-    if (!from_dist) {
+    if (!from_dist && src.n == 0) {
+      chunks.clear(); // a rank without particles launches nothing but still joins the all-reduce
+    }
+    if (!from_dist && src.n > 0) {
       const char* force = std::getenv("RGC_SPECTRUM_PATH");
       const bool  allow = !(force && std::strcmp(force, "gather") == 0);
       std::vector<std::vector<int>> rest;
+      int npair = 0;
+      for (auto& chunk : chunks) {
+        npair += (allow && pair_path_eligible(tp, bins_e_syn, chunk)) ? 1 : 0;
+      }
+      // one pair launch and nothing else: no intermediate synchronisation at all
+      deferred = npair == 1 && chunks.size() == 1;
       for (auto& chunk : chunks) {
         if (allow && pair_path_eligible(tp, bins_e_syn, chunk)) {
-          std::vector<double> acc;
           RGC_TRY(run_spectrum_pair(src.prtls, src.n, src.B0, src.g_syn, src.e_at, tp, bins_e_syn,
-                                    chunk, acc, &main_ms));
-          for (std::size_t s = 0; s < chunk.size(); ++s) {
-            acc_host[chunk[s]] = acc[s];
-          }
+                                    chunk, d_acc, &main_ms, deferred));
         } else {
           rest.push_back(std::move(chunk));
         }
@@ -507,8 +540,8 @@ namespace rgc {
       max_pad   = std::max<std::size_t>(max_pad, plans[k].table.size());
     }
     auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
-    const std::size_t off_acc   = 0;
-    const std::size_t off_out   = align(off_acc + nbins * sizeof(double));
+    const std::size_t off_map   = 0;
+    const std::size_t off_out   = align(off_map + max_slots * sizeof(int));
     const std::size_t off_afx   = align(off_out + max_slots * sizeof(double));
     const std::size_t off_table = align(off_afx + max_slots * sizeof(unsigned));
     const std::size_t off_part  = align(off_table + max_pad * sizeof(float2));
@@ -516,14 +549,12 @@ namespace rgc {
     void*             scratch   = nullptr;
     RGC_TRY(ensure_scratch(total, &scratch));
     char*   sbase   = static_cast<char*>(scratch);
-    double* d_acc   = reinterpret_cast<double*>(sbase + off_acc);
+    int*    d_map   = reinterpret_cast<int*>(sbase + off_map);
     double* d_out   = reinterpret_cast<double*>(sbase + off_out);
     auto*   d_afx   = reinterpret_cast<unsigned*>(sbase + off_afx);
     auto*   d_table = reinterpret_cast<float2*>(sbase + off_table);
     double* d_part  = reinterpret_cast<double*>(sbase + off_part);
 
-    RGC_CUDA(cudaMemsetAsync(d_acc, 0, nbins * sizeof(double), c.stream));
-    std::vector<double> out_host;
     for (std::size_t k = 0; k < plans.size(); ++k) {
       const LaunchPlan& lp = plans[k];
       RGC_CUDA(cudaMemcpyAsync(d_afx, lp.a_fx.data(), lp.a_fx.size() * sizeof(unsigned),
@@ -572,28 +603,25 @@ namespace rgc {
                                                                          nslots, d_out);
       RGC_CUDA(cudaGetLastError());
       count_launch(2);
-      out_host.resize(nslots);
-      RGC_CUDA(cudaMemcpyAsync(out_host.data(), d_out, nslots * sizeof(double),
-                               cudaMemcpyDeviceToHost, c.stream));
+      RGC_CUDA(cudaMemcpyAsync(d_map, lp.bin_of_slot.data(), nslots * sizeof(int),
+                               cudaMemcpyHostToDevice, c.stream));
+      RGC_TRY(launch_scatter_add(d_out, d_map, nslots, d_acc));
+      // the plan's host arrays and the events are reused by the next launch
       RGC_CUDA(cudaStreamSynchronize(c.stream));
       float ms = 0.f;
       RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]));
       main_ms += ms;
-      for (int s = 0; s < nslots; ++s) {
-        if (lp.bin_of_slot[s] >= 0) {
-          acc_host[lp.bin_of_slot[s]] = out_host[s];
-        }
-      }
     }
-    if (allreduce && c.nccl_comm && c.nranks > 1) {
-      RGC_CUDA(cudaMemcpyAsync(d_acc, acc_host.data(), nbins * sizeof(double),
-                               cudaMemcpyHostToDevice, c.stream));
+    if (allreduce) {
       RGC_TRY(allreduce_sum_f64(d_acc, nbins));
-      RGC_CUDA(cudaMemcpyAsync(acc_host.data(), d_acc, nbins * sizeof(double),
-                               cudaMemcpyDeviceToHost, c.stream));
     }
+    RGC_CUDA(cudaMemcpyAsync(acc_host.data(), d_acc, nbins * sizeof(double),
+                             cudaMemcpyDeviceToHost, c.stream));
     RGC_CUDA(cudaEventRecord(c.ev[1], c.stream));
     RGC_CUDA(cudaStreamSynchronize(c.stream));
+    if (deferred && src.n <= (std::size_t(1) << 27)) {
+      RGC_TRY(collect_pair_times(&main_ms));
+    }
     float total_ms = 0.f;
     RGC_CUDA(cudaEventElapsedTime(&total_ms, c.ev[0], c.ev[1]));
     c.last_ms[0] = total_ms;

@@ -208,3 +208,14 @@ def test_spectrum_pair_path_matches_gather_path(cabi, port, nbins, lo, hi, monke
     assert synth.rel_err(pair, gather) < 2e-6
     assert synth.rel_err(pair, want) < SPEC_RTOL
     assert np.all(pair[want == 0] == 0)
+
+
+def test_zero_active_particles(cabi):
+    """nactive == 0 (a rank that owns no particles): no launch, zeros, no fault"""
+    p = cabi.Particles(3).allocate(64)
+    p.n = 0
+    bins = cabi.logspace(0.01, 1e5, 200)
+    s32, s64 = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)
+    assert not s32.any() and not s64.any()
+    hist, counts, _ = cabi.energy_histogram(p, cabi.logspace(1e-2, 1e3, 50), log_spaced=False)
+    assert counts.sum() == 0 and not hist.any()

@@ -1,0 +1,72 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/dist_check.py
+
+Every rank owns shard_range(n, rank, world) of one seeded host population; the NCCL
+all-reduced spectrum / histogram of the sharded run must match the CPU oracle on the
+whole population (spectrum <= 1e-5 per bin, counts bit-exact and identical for every
+world size) and a one-rank run of the same library (<= 1e-6: the hinge sums are float
+per piece of <= 1024 sorted particles, and the pieces depend on the partition)."""
+import os
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import oracle
+from ragnar_b200 import cabi
+from ragnar_b200 import dist as rdist
+from tests import synth
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+cabi.init(local)
+n = 1_000_003
+U, E, B = synth.full3d(n, seed=17)
+bins = cabi.logspace(1e-3, 1e6, 1000)
+gbins = cabi.logspace(1e-2, 1e3, 200)
+consts = (1.3, 2.0, 0.7)
+
+# one-rank reference run of the same library, before the communicator exists
+if rank == 0:
+    p_all = cabi.Particles(3).from_columns(U=U, E=E, B=B)
+    solo_spec = cabi.sync_spectrum_particles(p_all, bins, *consts)[1]
+    solo_hist = cabi.energy_histogram(p_all, gbins, log_spaced=True, fourvel=True)
+    p_all.release()
+
+rdist.install_communicator(cabi, dist)
+lo, cnt = rdist.shard_range(n, rank, world)
+hi = lo + cnt
+p = cabi.Particles(3).from_columns(U=[u[lo:hi] for u in U], E=[e[lo:hi] for e in E],
+                                   B=[b[lo:hi] for b in B])
+spec = cabi.sync_spectrum_particles(p, bins, *consts)[1]
+hist, counts, h64 = cabi.energy_histogram(p, gbins, log_spaced=True, fourvel=True)
+# a rank that owns no particles still joins the exchange
+empty = cabi.Particles(3).allocate(16)
+empty.n = 0
+spec0 = cabi.sync_spectrum_particles(p if rank == 0 else empty, bins, *consts)[1]
+ok = True
+if rank == 0:
+    _, want = oracle.port.sync_spectrum_particles(U, E, B, bins, *consts)
+    big = want >= 1e-6 * want.max()
+    err = float(np.max(np.abs(spec[big] - want[big]) / want[big]))
+    _, want_h64, want_c = oracle.port.energy_distribution(*U, gbins, True, True)
+    nz = want_h64 > 0
+    herr = float(np.max(np.abs(h64[nz] - want_h64[nz]) / want_h64[nz]))
+    add = float(np.max(np.abs(spec[big] - solo_spec[big]) / solo_spec[big]))
+    ok = (err < 1e-5 and herr < 1e-5 and np.array_equal(counts, want_c)
+          and np.array_equal(counts, solo_hist[1]) and add < 1e-6
+          and np.array_equal(spec == 0, want == 0) and np.all(np.isfinite(spec0)))
+    print(f"[dist_check] world={world} n={n}: spectrum rel err vs oracle {err:.2e}, "
+          f"weighted hist {herr:.2e}, counts bit-exact={np.array_equal(counts, want_c)}, "
+          f"sharded vs one-rank spectrum {add:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
+flag = torch.tensor([0 if ok else 1], device="cuda")
+dist.all_reduce(flag)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(int(flag.item() != 0))
