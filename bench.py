@@ -46,6 +46,15 @@ GAMMA_BINS = (1e-2, 1e3, 200)
 CONSTS = (1.0, 1.0, 1.0)  # B0, g_syn, e_syn_at_g_syn
 SEED = 123
 CPU_SAMPLE = 1_000_000  # particles per CPU-baseline step (x 200 bins = 2e8 evals)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload, from the
+# committed `ncu --set full` capture profiles/r1_ncu_full_v4_summary.json (not measurable
+# live: a number printed under a profiler is never a bench value)
+NCU_TRAFFIC_BYTES = {
+    "sync_pair_kernel": 0.800283e9 + 5.590e6,
+    "sync_prologue_kernel": 3.600577e9 + 945.70e6,
+    "sync_sort_kernel": 1.009416e9 + 763.17e6,
+    "energy_hist_kernel": 1.200043e9 + 4.23e6,
+}
 
 
 def workload_config(n_per_gpu: int, nbins: int, ngpus: int) -> dict:
@@ -329,10 +338,16 @@ def run_ours(args) -> None:
     achieved_tflops = evals_per_launch * 4 / (spec_ms * 1e-3) / 1e12
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    default_workload = n == N_PER_GPU and nbins == NBINS
+
+    def traffic(kernel):
+        return NCU_TRAFFIC_BYTES[kernel] if default_workload else None
     roofline = {
         "kernel": "sync_pair_kernel", "bound": "fp32",
         "achieved": achieved_tflops, "peak": ffma_peak_tflops, "unit": "TFLOP/s",
-        "frac": achieved_tflops / ffma_peak_tflops, "traffic": None,
+        "frac": achieved_tflops / ffma_peak_tflops, "traffic": traffic("sync_pair_kernel"),
+        "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r1_ncu_full_v4_summary.json); "
+                        "algorithmic: 8 B per particle = 0.8e9",
         "peak_source": "FFMA issue rate measured on this device by rgc_measure_peak(0) in this "
                        "run (of measured); 4 flop per evaluation = FFMA.SAT + FFMA",
         "evals_per_s": evals_per_launch / (spec_ms * 1e-3), "ms_per_launch": spec_ms,
@@ -344,21 +359,21 @@ def run_ours(args) -> None:
     roofline_pro = {
         "kernel": "sync_prologue_kernel", "bound": "hbm",
         "achieved": n * 46 / (pro_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": n * 46 / (pro_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+        "frac": n * 46 / (pro_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic("sync_prologue_kernel"),
         "peak_source": hbm_src, "ms_per_launch": pro_ms,
         "bytes_per_particle": "36 read (U,E,B) + 10 written (fc, w, bucket)",
     }
     roofline_sort = {
         "kernel": "sync_sort_kernel (+ pair_colscan_kernel)", "bound": "hbm",
         "achieved": n * 18 / (sort_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": n * 18 / (sort_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+        "frac": n * 18 / (sort_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic("sync_sort_kernel"),
         "peak_source": hbm_src, "ms_per_launch": sort_ms,
         "bytes_per_particle": "10 read (fc, w, bucket) + 8 written (fc, w in global bucket order)",
     }
     roofline_hist = {
         "kernel": "energy_hist_kernel", "bound": "hbm",
         "achieved": n * 12 / (hist_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": n * 12 / (hist_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+        "frac": n * 12 / (hist_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic("energy_hist_kernel"),
         "peak_source": hbm_src,
         "particles_per_s": n / (hist_ms * 1e-3), "ms_per_launch": hist_ms,
     }

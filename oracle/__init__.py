@@ -56,11 +56,23 @@ def ref_available() -> bool:
     return any(REF_DIR.glob("ragnar_ref.*.so")) and any(REF_DIR.glob("ragnar_ref64.*.so"))
 
 
+_ref_modules: dict = {}
+
+
 def _import_ref(name: str):
+    """Imports and initialises the module once; the reference's Initialize() banner
+    ("Kokkos is already initialized" on a second call) is kept off stdout."""
+    if name in _ref_modules:
+        return _ref_modules[name]
+    import contextlib
+    import io
+
     if str(REF_DIR) not in sys.path:
         sys.path.insert(0, str(REF_DIR))
     mod = importlib.import_module(name)
-    mod.Initialize()
+    with contextlib.redirect_stdout(io.StringIO()):
+        mod.Initialize()
+    _ref_modules[name] = mod
     return mod
 
 
