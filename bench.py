@@ -57,7 +57,18 @@ NCU_TRAFFIC_BYTES = {
 }
 
 
-def workload_config(n_per_gpu: int, nbins: int, ngpus: int) -> dict:
+def workload_config(n_per_gpu: int, nbins: int, ngpus: int, population: str = "config3") -> dict:
+    if population != "config3":
+        return {
+            "workload": "SynchrotronSpectrum_3D + Particles.energyDistribution, BASELINE configs[4] "
+                        "(at scale: full-3D population)",
+            "particles_per_gpu": n_per_gpu, "photon_bins": nbins,
+            "photon_bin_range_mec2": list(PHOTON_BINS), "gamma_beta_bins": list(GAMMA_BINS),
+            "population": "isotropic U, |U|~u^-2 on [1,100], |B| in [0.5,2] isotropic, "
+                          "E = 0.1 B x random (device Philox4x32-10, seed 123)",
+            "sharding": f"particles/{ngpus} ranks, NCCL all-reduce of spectra" if ngpus > 1 else "none",
+            "cache": "inputs_larger_than_L2",
+        }
     return {
         "workload": "SynchrotronSpectrum_3D + Particles.energyDistribution, BASELINE configs[2]",
         "particles_per_gpu": n_per_gpu,
@@ -226,7 +237,7 @@ def run_ours(args) -> None:
     table = cabi.tabulate_ffunc()
     prtls = cabi.Particles(3).allocate(n)
     # rank r owns global particle indices [r*n, (r+1)*n) of one Philox stream
-    prtls.generate(0, SEED, rank * n, 0, n, 1.0, 100.0)
+    prtls.generate(0 if args.population == "config3" else 1, SEED, rank * n, 0, n, 1.0, 100.0)
     cabi.synchronize()
 
     def barrier():
@@ -400,7 +411,7 @@ def run_ours(args) -> None:
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 pair terms, fp64 prologue and accumulation",
-        "data": "synthetic", "config": workload_config(n, nbins, world),
+        "data": "synthetic", "config": workload_config(n, nbins, world, args.population),
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "roofline_prologue_kernel": roofline_pro,
         "roofline_sort_kernel": roofline_sort,
@@ -421,10 +432,16 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--particles", type=int, default=N_PER_GPU, help="particles per GPU")
     ap.add_argument("--bins", type=int, default=NBINS)
+    ap.add_argument("--bins-lo", type=float, default=PHOTON_BINS[0])
+    ap.add_argument("--bins-hi", type=float, default=PHOTON_BINS[1])
+    ap.add_argument("--population", choices=["config3", "full3d"], default="config3",
+                    help="config3: U1~u^-2, E=0, B unit isotropic; full3d: BASELINE configs[4]")
     ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global PHOTON_BINS
+    PHOTON_BINS = (args.bins_lo, args.bins_hi)
     if args.impl == "reference":
         run_reference(args)
     else:
