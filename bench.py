@@ -425,6 +425,7 @@ def run_ours(args) -> None:
 
 
 def main() -> None:
+    global PHOTON_BINS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -440,7 +441,6 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    global PHOTON_BINS
     PHOTON_BINS = (args.bins_lo, args.bins_hi)
     if args.impl == "reference":
         run_reference(args)
