@@ -132,7 +132,10 @@ namespace rgc {
           ux[h] = uy[h] = uz[h] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      float lo_f = 0.0f, hi_f = 0.0f;
+      float    lo_f = 0.0f, hi_f = 0.0f;
+      unsigned lo_c = 0, hi_c = 0;
+      // full tiles (all but the last) carry no per-particle bounds checks
+      const bool full = base + kHTile <= P.nprtl;
 #pragma unroll
       for (int h = 0; h < kPerThread / 4; ++h) {
         const std::size_t i0 = base + (std::size_t)h * (kHThreads * 4) + (std::size_t)tid * 4;
@@ -141,7 +144,7 @@ namespace rgc {
         const float*      pz = reinterpret_cast<const float*>(&uz[h]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (i0 + k >= P.nprtl) {
+          if (!full && i0 + k >= P.nprtl) {
             continue;
           }
           // reference particles.cpp:228-230, float, left to right, unfused
@@ -166,10 +169,10 @@ namespace rgc {
             w = rsqrtf(X); // 1/energy; the reference rounds 1.0/energy to float
           }
           if (idx == 0) {
-            lo_cnt += 1;
+            lo_c += 1u;
             lo_f += w;
           } else if (idx == n - 1) {
-            hi_cnt += 1;
+            hi_c += 1u;
             hi_f += w;
           } else {
             if (COUNTS) {
@@ -186,6 +189,8 @@ namespace rgc {
           }
         }
       }
+      lo_cnt += lo_c;
+      hi_cnt += hi_c;
       if (WEIGHTED) {
         lo_sum += (double)lo_f;
         hi_sum += (double)hi_f;

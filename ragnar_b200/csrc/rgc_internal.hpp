@@ -138,6 +138,8 @@ namespace rgc {
                          bool defer_sync);
   // after the caller's own stream synchronisation: kernel times of a deferred pass
   int  collect_pair_times(float* main_ms);
+  bool pair_single_pass(std::size_t n); // n particles fit one pipeline pass
+  void pair_release_plans();            // frees the cached device plans (rgc_finalize)
   // d_acc[binmap[s]] += src[s] for every slot with binmap[s] >= 0
   int  launch_scatter_add(const double* src, const int* binmap, int nslots, double* d_acc);
 } // namespace rgc

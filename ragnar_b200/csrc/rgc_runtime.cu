@@ -308,6 +308,7 @@ extern "C" {
     cudaDeviceSynchronize();
     rgc_comm_destroy();
     io_release_lanes();
+    pair_release_plans();
     for (int s = 0; s < kNumStages; ++s) {
       if (c.stage[s]) {
         cudaFreeHost(c.stage[s]);

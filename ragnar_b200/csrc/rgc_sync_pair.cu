@@ -1035,6 +1035,95 @@ namespace rgc {
     }
   }
 
+  // Plans are kept with their device copy (slot tables, hinge and line coefficients):
+  // a repeated call with the same photon bins and F table uploads nothing.
+  struct CachedPlan {
+    std::vector<float>  key_bins;  // e_syn of the chunk's bins, in slot order
+    std::vector<int>    key_index; // their indices in the caller's bin array
+    std::vector<double> key_tx, key_y;
+    PairPlan            pp;
+    char*               dev { nullptr };
+    std::size_t         off_map { 0 }, off_si { 0 }, off_sf { 0 }, off_dh { 0 }, off_vs { 0 };
+  };
+  static std::vector<CachedPlan>& plan_cache() {
+    static std::vector<CachedPlan> cache;
+    return cache;
+  }
+
+  void pair_release_plans() {
+    for (auto& e : plan_cache()) {
+      if (e.dev) {
+        cudaFree(e.dev);
+      }
+    }
+    plan_cache().clear();
+  }
+
+  static int cached_pair_plan(const TablePlan& tp, const float* bins_e_syn,
+                              const std::vector<int>& bins, const CachedPlan** out) {
+    auto&              cache = plan_cache();
+    std::vector<float> kb(bins.size());
+    for (std::size_t s = 0; s < bins.size(); ++s) {
+      kb[s] = bins_e_syn[bins[s]];
+    }
+    for (const auto& e : cache) {
+      if (e.key_index == bins && e.key_bins.size() == kb.size() &&
+          std::memcmp(e.key_bins.data(), kb.data(), kb.size() * sizeof(float)) == 0 &&
+          e.key_tx == tp.tx && e.key_y == tp.y) {
+        *out = &e;
+        return RGC_OK;
+      }
+    }
+    if (cache.size() >= 8) {
+      RGC_CUDA(cudaStreamSynchronize(ctx().stream));
+      cudaFree(cache.front().dev);
+      cache.erase(cache.begin());
+    }
+    CachedPlan e;
+    e.key_bins  = kb;
+    e.key_index = bins;
+    e.key_tx    = tp.tx;
+    e.key_y     = tp.y;
+    make_pair_plan(tp, bins_e_syn, bins, e.pp);
+    const PairPlan& pp = e.pp;
+    auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
+    e.off_map = 0;
+    e.off_si  = align(e.off_map + pp.nslots * sizeof(int));
+    e.off_sf  = align(e.off_si + pp.nslots * sizeof(int2));
+    e.off_dh  = align(e.off_sf + pp.nslots * sizeof(float2));
+    e.off_vs  = align(e.off_dh + pp.n_pad * sizeof(float4));
+    const std::size_t total = align(e.off_vs + pp.n_pad * sizeof(double2));
+    RGC_CUDA(cudaMalloc(reinterpret_cast<void**>(&e.dev), total));
+    cudaStream_t st = ctx().stream;
+    RGC_CUDA(cudaMemcpyAsync(e.dev + e.off_map, pp.bin_of_slot.data(), pp.nslots * sizeof(int),
+                             cudaMemcpyHostToDevice, st));
+    RGC_CUDA(cudaMemcpyAsync(e.dev + e.off_si, pp.slot_i.data(), pp.nslots * sizeof(int2),
+                             cudaMemcpyHostToDevice, st));
+    RGC_CUDA(cudaMemcpyAsync(e.dev + e.off_sf, pp.slot_f.data(), pp.nslots * sizeof(float2),
+                             cudaMemcpyHostToDevice, st));
+    RGC_CUDA(cudaMemcpyAsync(e.dev + e.off_dh, pp.coef_dh.data(), pp.n_pad * sizeof(float4),
+                             cudaMemcpyHostToDevice, st));
+    RGC_CUDA(cudaMemcpyAsync(e.dev + e.off_vs, pp.coef_vs.data(), pp.n_pad * sizeof(double2),
+                             cudaMemcpyHostToDevice, st));
+    cache.push_back(std::move(e));
+    *out = &cache.back();
+    return RGC_OK;
+  }
+
+  // particles per pipeline pass (bounds the staged and sorted arrays: 18 B per particle)
+  static std::size_t pair_pass_max() {
+    std::size_t chunk_max = std::size_t(1) << 27;
+    if (const char* pm = std::getenv("RGC_PAIR_PASS_MAX")) { // test knob
+      const long long v = std::atoll(pm);
+      if (v >= kPTile && (std::size_t)v < chunk_max) {
+        chunk_max = (std::size_t)v / kPTile * kPTile;
+      }
+    }
+    return chunk_max;
+  }
+
+  bool pair_single_pass(std::size_t n) { return n <= pair_pass_max(); }
+
   template <int G>
   static int launch_pair_g(dim3 grid, std::size_t smem, cudaStream_t st, const PairParams& P) {
     auto kern = sync_pair_kernel<G>;
@@ -1064,9 +1153,10 @@ namespace rgc {
                         float e_at, const TablePlan& tp, const float* bins_e_syn,
                         const std::vector<int>& bins, double* d_acc, float* main_ms,
                         bool defer_sync) {
-    auto&    c = ctx();
-    PairPlan pp;
-    make_pair_plan(tp, bins_e_syn, bins, pp);
+    auto&             c  = ctx();
+    const CachedPlan* cp = nullptr;
+    RGC_TRY(cached_pair_plan(tp, bins_e_syn, bins, &cp));
+    const PairPlan& pp = cp->pp;
     if (pp.nb >= kPMaxBuckets || pp.nbp > kPMaxBuckets) {
       return fail(RGC_ERR_INVALID, "internal: %d buckets exceed the pair path's limit", pp.nb);
     }
@@ -1077,7 +1167,7 @@ namespace rgc {
     }
     // particles are processed in passes so the staged and sorted (fc, w, key) stay
     // bounded (18 B per particle); pass results are summed on the host in pass order
-    const std::size_t chunk_max = std::size_t(1) << 27;
+    const std::size_t chunk_max = pair_pass_max();
     const std::size_t cnt0      = std::min(n, chunk_max);
     const char* sr          = std::getenv("RGC_SORT_RANK"); // "ballot": guaranteed-order ranking
     const bool  atomic_rank = !(sr && std::strcmp(sr, "ballot") == 0);
@@ -1102,12 +1192,7 @@ namespace rgc {
     const int         pair_ctas   = c.sm_count * 2;
     const std::size_t max_pieces  = cnt0 / kPieceLen + (std::size_t)pp.nbp + 2;
     auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
-    const std::size_t off_map  = 0;
-    const std::size_t off_si   = align(off_map + pp.nslots * sizeof(int));
-    const std::size_t off_sf   = align(off_si + pp.nslots * sizeof(int2));
-    const std::size_t off_dh   = align(off_sf + pp.nslots * sizeof(float2));
-    const std::size_t off_vs   = align(off_dh + pp.n_pad * sizeof(float4));
-    const std::size_t off_msum = align(off_vs + pp.n_pad * sizeof(double2));
+    const std::size_t off_msum = 0;
     const std::size_t off_out  = align(off_msum + 2 * pp.nb * sizeof(double));
     const std::size_t off_part = align(off_out + pp.nslots * sizeof(double));
     const std::size_t off_tot  = align(off_part + (std::size_t)pair_ctas * pp.nslots * sizeof(double));
@@ -1120,20 +1205,10 @@ namespace rgc {
     void*             scratch  = nullptr;
     RGC_TRY(ensure_scratch(total, &scratch));
     char* sb = static_cast<char*>(scratch);
-    RGC_CUDA(cudaMemcpyAsync(sb + off_map, pp.bin_of_slot.data(), pp.nslots * sizeof(int),
-                             cudaMemcpyHostToDevice, c.stream));
-    RGC_CUDA(cudaMemcpyAsync(sb + off_si, pp.slot_i.data(), pp.nslots * sizeof(int2),
-                             cudaMemcpyHostToDevice, c.stream));
-    RGC_CUDA(cudaMemcpyAsync(sb + off_sf, pp.slot_f.data(), pp.nslots * sizeof(float2),
-                             cudaMemcpyHostToDevice, c.stream));
-    RGC_CUDA(cudaMemcpyAsync(sb + off_dh, pp.coef_dh.data(), pp.n_pad * sizeof(float4),
-                             cudaMemcpyHostToDevice, c.stream));
-    RGC_CUDA(cudaMemcpyAsync(sb + off_vs, pp.coef_vs.data(), pp.n_pad * sizeof(double2),
-                             cudaMemcpyHostToDevice, c.stream));
     PairParams P {};
-    P.slot_i   = reinterpret_cast<const int2*>(sb + off_si);
-    P.slot_f   = reinterpret_cast<const float2*>(sb + off_sf);
-    P.coef_dh  = reinterpret_cast<const float4*>(sb + off_dh);
+    P.slot_i   = reinterpret_cast<const int2*>(cp->dev + cp->off_si);
+    P.slot_f   = reinterpret_cast<const float2*>(cp->dev + cp->off_sf);
+    P.coef_dh  = reinterpret_cast<const float4*>(cp->dev + cp->off_dh);
     P.n_pad    = pp.n_pad;
     P.nb       = pp.nb;
     P.nbp      = pp.nbp;
@@ -1207,10 +1282,10 @@ namespace rgc {
       RGC_CUDA(cudaGetLastError());
       pair_final_kernel<<<(pp.nslots + kPWarps - 1) / kPWarps, kPThreads, 0, c.stream>>>(
         P.partials, pair_ctas, pp.nslots, P.slot_i, P.slot_f,
-        reinterpret_cast<const double2*>(sb + off_vs), d_msum, pp.nb, d_out);
+        reinterpret_cast<const double2*>(cp->dev + cp->off_vs), d_msum, pp.nb, d_out);
       RGC_CUDA(cudaGetLastError());
       count_launch(6);
-      RGC_TRY(launch_scatter_add(d_out, reinterpret_cast<const int*>(sb + off_map), pp.nslots,
+      RGC_TRY(launch_scatter_add(d_out, reinterpret_cast<const int*>(cp->dev + cp->off_map), pp.nslots,
                                  d_acc));
       if (defer_sync && n <= chunk_max) {
         // single pass: the caller synchronises once and then collects the times

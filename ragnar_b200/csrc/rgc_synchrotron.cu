@@ -619,7 +619,7 @@ namespace rgc {
                              cudaMemcpyDeviceToHost, c.stream));
     RGC_CUDA(cudaEventRecord(c.ev[1], c.stream));
     RGC_CUDA(cudaStreamSynchronize(c.stream));
-    if (deferred && src.n <= (std::size_t(1) << 27)) {
+    if (deferred && pair_single_pass(src.n)) {
       RGC_TRY(collect_pair_times(&main_ms));
     }
     float total_ms = 0.f;

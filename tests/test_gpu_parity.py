@@ -219,3 +219,21 @@ def test_zero_active_particles(cabi):
     assert not s32.any() and not s64.any()
     hist, counts, _ = cabi.energy_histogram(p, cabi.logspace(1e-2, 1e3, 50), log_spaced=False)
     assert counts.sum() == 0 and not hist.any()
+
+
+def test_spectrum_multi_pass(cabi, port, monkeypatch):
+    """populations larger than one pipeline pass (2^27 particles in production; forced
+    down to 8192 here): several passes accumulate on the device into the same result"""
+    n = 50_000
+    U, E, B = synth.full3d(n, seed=5)
+    bins = cabi.logspace(0.01, 1e5, 200)
+    p = _particles(cabi, U, E, B)
+    one = cabi.sync_spectrum_particles(p, bins, 1.3, 2.0, 0.7)[1]
+    monkeypatch.setenv("RGC_PAIR_PASS_MAX", "8192")
+    many = cabi.sync_spectrum_particles(p, bins, 1.3, 2.0, 0.7)[1]
+    monkeypatch.delenv("RGC_PAIR_PASS_MAX")
+    _, want = port.sync_spectrum_particles(U, E, B, bins, 1.3, 2.0, 0.7)
+    big = want >= 1e-6 * want.max()
+    assert np.max(np.abs(many[big] - want[big]) / want[big]) < SPEC_RTOL
+    assert np.max(np.abs(many[big] - one[big]) / one[big]) < 1e-6
+    assert np.array_equal(many == 0, want == 0)
