@@ -292,6 +292,13 @@ int rgc_h5_write_array(const char* filename, const char* dsetname, const rgc_buf
 int rgc_tristan_read_particles(const char* path, size_t step, unsigned sp, size_t start,
                                size_t size, size_t stride, int ignore_coords, int dim,
                                rgc_particles_t** out, size_t* ntotal, size_t* nread);
+/* Sharded read of the multi-GPU path (not in the reference): exactly particles
+ * [start, start + count) of species sp, count > 0, start + count <= ntotal — the
+ * reference's selection rejects a range that ends at the last particle
+ * (tristan-v2.cpp:126-128), which a rank's contiguous share must be able to do. */
+int rgc_tristan_read_range(const char* path, size_t step, unsigned sp, size_t start,
+                           size_t count, int ignore_coords, int dim, rgc_particles_t** out,
+                           size_t* ntotal);
 /* writes a synthetic Tristan-v2 particle file (test / bench fixture generator):
  * datasets named as above for species sp, n floats each, contiguous float32.
  * columns = x,y,z (only when with_coords), u,v,w, ex,ey,ez, bx,by,bz; columns[k]

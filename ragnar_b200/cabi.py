@@ -91,6 +91,8 @@ SIGNATURES = {
     "rgc_h5_write_array": (C.c_int, [C.c_char_p, C.c_char_p, _vp]),
     "rgc_tristan_read_particles": (C.c_int, [C.c_char_p, _sz, C.c_uint, _sz, _sz, _sz, C.c_int,
                                              C.c_int, _vpp, C.POINTER(_sz), C.POINTER(_sz)]),
+    "rgc_tristan_read_range": (C.c_int, [C.c_char_p, _sz, C.c_uint, _sz, _sz, C.c_int, C.c_int,
+                                         _vpp, C.POINTER(_sz)]),
     "rgc_tristan_write_species": (C.c_int, [C.c_char_p, _sz, C.c_uint, _sz, C.c_int,
                                             C.POINTER(_f32p), C.c_int]),
 }
@@ -411,6 +413,18 @@ def tristan_read_particles(path: str, step: int, sp: int, start=0, size=0, strid
                                            int(ignore_coords), dim, C.byref(p.h),
                                            C.byref(ntotal), C.byref(nread)))
     p.n = nread.value
+    return p, ntotal.value
+
+
+def tristan_read_range(path: str, step: int, sp: int, start: int, count: int,
+                       ignore_coords=False, dim=3):
+    """exactly particles [start, start + count) (sharded multi-GPU reads) -> (Particles, ntotal)"""
+    p = Particles.__new__(Particles)
+    p.h = _vp()
+    ntotal = _sz()
+    check(lib().rgc_tristan_read_range(path.encode(), step, sp, start, count, int(ignore_coords),
+                                       dim, C.byref(p.h), C.byref(ntotal)))
+    p.n = count
     return p, ntotal.value
 
 

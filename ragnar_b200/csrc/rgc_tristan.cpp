@@ -432,12 +432,18 @@ int rgc_h5_write_array(const char* filename, const char* dsetname, const rgc_buf
 }
 
 // ------------------------------------------------------------ Tristan-v2 plugin
-int rgc_tristan_read_particles(const char* path, size_t step, unsigned sp, size_t start,
+// range_mode: exactly [start, start + size) with start + size <= ntotal (the sharded
+// reader of the multi-GPU path); otherwise the reference's selection rules
+static int read_particles_impl(const char* path, size_t step, unsigned sp, size_t start,
                                size_t size, size_t stride, int ignore_coords, int dim,
-                               rgc_particles_t** out, size_t* ntotal_out, size_t* nread_out) {
+                               rgc_particles_t** out, size_t* ntotal_out, size_t* nread_out,
+                               bool range_mode) {
   RGC_REQUIRE_INIT();
   if (!path || !out) {
     return fail(RGC_ERR_INVALID, "rgc_tristan_read_particles: bad argument");
+  }
+  if (range_mode && (stride != 1 || size == 0)) {
+    return fail(RGC_ERR_INVALID, "rgc_tristan_read_range: count must be > 0");
   }
   if (dim < 1 || dim > 3) {
     return fail(RGC_ERR_INVALID, "dim must be 1, 2 or 3 (got %d)", dim);
@@ -458,7 +464,7 @@ int rgc_tristan_read_particles(const char* path, size_t step, unsigned sp, size_
       return fail(RGC_ERR_IO, "Dataset is not 1D");
     }
     const std::uint64_t ntotal = xds.dims[0];
-    if (start + size >= ntotal) {
+    if (range_mode ? start + size > ntotal : start + size >= ntotal) {
       return fail(RGC_ERR_INVALID, "start + size >= total number of particles");
     }
     const std::uint64_t nparticles = size == 0 ? ntotal / stride : size;
@@ -510,6 +516,21 @@ int rgc_tristan_read_particles(const char* path, size_t step, unsigned sp, size_
   })
   *out = prtls;
   return RGC_OK;
+}
+
+int rgc_tristan_read_particles(const char* path, size_t step, unsigned sp, size_t start,
+                               size_t size, size_t stride, int ignore_coords, int dim,
+                               rgc_particles_t** out, size_t* ntotal_out, size_t* nread_out) {
+  return read_particles_impl(path, step, sp, start, size, stride, ignore_coords, dim, out,
+                             ntotal_out, nread_out, false);
+}
+
+int rgc_tristan_read_range(const char* path, size_t step, unsigned sp, size_t start,
+                           size_t count, int ignore_coords, int dim, rgc_particles_t** out,
+                           size_t* ntotal_out) {
+  size_t nread = 0;
+  return read_particles_impl(path, step, sp, start, count, 1, ignore_coords, dim, out,
+                             ntotal_out, &nread, true);
 }
 
 int rgc_tristan_write_species(const char* path, size_t step, unsigned sp, size_t n,
