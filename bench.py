@@ -389,6 +389,42 @@ def run_ours(args) -> None:
         "particles_per_s": n / (hist_ms * 1e-3), "ms_per_launch": hist_ms,
     }
 
+    # ---- the other single-GPU BASELINE configs, N = 1 only (extra keys, not the metric):
+    # configs[1] histogram on the contended population (u in [5e-3, 2e3]: ~53 % of the
+    # particles fall into clamp bin 0) and configs[0] FromDist latency
+    other = None
+    if world == 1 and not args.no_cpu_baseline:
+        p2 = cabi.Particles(3).allocate(n)
+        p2.generate(2, SEED, 0, 0, n, 5e-3, 2e3)
+        cabi.synchronize()
+        for _ in range(3):
+            cabi.energy_histogram(p2, gbins, True, True, want_counts=False)
+        ms2 = []
+        for _ in range(10):
+            cabi.energy_histogram(p2, gbins, True, True, want_counts=False)
+            ms2.append(cabi.last_kernel_ms()[1])
+        h2 = statistics.mean(ms2)
+        p2.release()
+        gb = cabi.logspace(1, 100, 200)
+        fdist = cabi.generator_eval(0, [-2.0, 1.0, 100.0], gb)
+        b1 = cabi.logspace(0.01, 1e7, 200)
+        cabi.sync_spectrum_dist(gb, fdist, True, b1, 1.0, 1.0, table=table)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            cabi.sync_spectrum_dist(gb, fdist, True, b1, 1.0, 1.0, table=table)
+        fd_us = 1e6 * (time.perf_counter() - t0) / 20
+        other = {
+            "config1_histogram": {
+                "workload": "Particles.energyDistribution, 1e8 power-law electrons u in [5e-3, 2e3] "
+                            "into Logbins(1e-2, 1e3, 200)" if n == N_PER_GPU else f"{n} particles",
+                "ms_per_launch": h2, "particles_per_s": n / (h2 * 1e-3),
+                "hbm_GBps": n * 12 / (h2 * 1e-3) / 1e9, "frac_of_hbm_peak": n * 12 / (h2 * 1e-3) / 1e9 / hbm_peak},
+            "config0_fromdist": {
+                "workload": "SynchrotronSpectrumFromDist: PlawGenerator(-2,1,100) on Logbins(1,100,200) -> "
+                            "200 photon Logbins(0.01,1e7)", "evals": 40000,
+                "us_per_call_host_wall": fd_us, "note": "latency-bound; F table cached"},
+        }
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -417,6 +453,7 @@ def run_ours(args) -> None:
         "roofline_sort_kernel": roofline_sort,
         "roofline_histogram_kernel": roofline_hist,
         "cpu_baseline": cpu_baseline,
+        "other_configs": other,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
