@@ -526,7 +526,7 @@ namespace rgc {
     unsigned      parity = 0;
     for (int tile = t0; tile < t1; ++tile) {
       // ---- per-warp bucket cursors, zeroed; the previous tile's write-out is
-      // complete once every warp has passed this barrier
+      // complete once every warp has passed the barrier below
       for (int i = tid; i < kPWarps * nbp; i += kPThreads) {
         hw[i] = 0;
       }
@@ -537,6 +537,7 @@ namespace rgc {
       // bucket (warp w owns tile entries [512 w, 512 w + 512), 32 per step)
       int*     cur = hw + warp * nbp;
       unsigned rank_pack[kPSteps / 2]; // u16 ranks, two per register
+      unsigned key_pack[kPSteps / 2];  // the keys of pass A, kept for pass B
       if (ATOMIC_RANK) {
 #pragma unroll
         for (int st = 0; st < kPSteps; ++st) {
@@ -547,8 +548,10 @@ namespace rgc {
           }
           if ((st & 1) == 0) {
             rank_pack[st >> 1] = rk;
+            key_pack[st >> 1]  = key;
           } else {
             rank_pack[st >> 1] |= rk << 16;
+            key_pack[st >> 1] |= key << 16;
           }
         }
       } else {
@@ -625,8 +628,11 @@ namespace rgc {
         for (int i = 0; i < kPer; ++i) {
           const int b = tid * kPer + i;
           if (b < nb) {
-            seg_off[b] = run;
-            int r2     = run;
+            // global position of sorted entry i of bucket b: i + (gcur[b] - run); the
+            // row's cursor moves on by this tile's count right away
+            seg_off[b] = gcur[b] - run;
+            gcur[b] += tcnt[i];
+            int r2 = run;
 #pragma unroll
             for (int wq = 0; wq < kPWarps; ++wq) {
               const int c      = hw[wq * nbp + b];
@@ -647,7 +653,8 @@ namespace rgc {
 #pragma unroll
         for (int step = 0; step < kPSteps; ++step) {
           const int      idx = warp * (kPTile / kPWarps) + step * 32 + lane;
-          const unsigned key = stage_k[idx];
+          const unsigned key = ATOMIC_RANK ? (key_pack[step >> 1] >> ((step & 1) * 16)) & 0xffffu
+                                           : (unsigned)stage_k[idx];
           if (key != kInvalidKey) {
             const unsigned rk  = (rank_pack[step >> 1] >> ((step & 1) * 16)) & 0xffffu;
             const unsigned pos = (unsigned)basep[key] + rk;
@@ -667,18 +674,11 @@ namespace rgc {
       {
         const int total = scan_tmp[2 * kPWarps];
         for (int i = tid; i < total; i += kPThreads) {
-          const int k = sorted_k[i];
-          P.sorted[gcur[k] + (i - seg_off[k])] = sorted[i];
+          P.sorted[i + seg_off[sorted_k[i]]] = sorted[i];
         }
       }
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < kPer; ++i) {
-        const int b = tid * kPer + i;
-        if (b < nb) {
-          gcur[b] += tcnt[i];
-        }
-      }
+      // no barrier here: the next tile's first barrier (after the cursor reset, which
+      // touches nothing the write-out reads) orders everything that follows
     }
   }
 
