@@ -522,7 +522,8 @@ namespace rgc {
       gcur[b] = bstart[b] + P.counts[(std::size_t)b * P.rows + row];
     }
 
-    constexpr int kPer = kPMaxBuckets / kPThreads; // buckets per thread in the scan
+    constexpr int kPer = kPMaxBuckets / kPThreads; // most buckets per thread in the scan
+    const int     bpt    = (nb + kPThreads - 1) / kPThreads;
     unsigned      parity = 0;
     for (int tile = t0; tile < t1; ++tile) {
       // ---- per-warp bucket cursors, zeroed; the previous tile's write-out is
@@ -588,14 +589,16 @@ namespace rgc {
       __syncthreads();
       // ---- scan: tile totals per bucket -> first sorted entry of every bucket
       // (seg_off) and of every (warp, bucket)
+      // (bpt consecutive buckets per thread: 1 for up to 256 buckets, so the scan is
+      // spread over all warps)
       int tcnt[kPer];
       {
         int sum = 0;
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
-          const int b   = tid * kPer + i;
+          const int b   = tid * bpt + i;
           int       tot = 0;
-          if (b < nb) {
+          if (i < bpt && b < nb) {
 #pragma unroll
             for (int wq = 0; wq < kPWarps; ++wq) {
               tot += hw[wq * nbp + b];
@@ -626,8 +629,8 @@ namespace rgc {
         int run = warp_base + incl - sum;
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
-          const int b = tid * kPer + i;
-          if (b < nb) {
+          const int b = tid * bpt + i;
+          if (i < bpt && b < nb) {
             // global position of sorted entry i of bucket b: i + (gcur[b] - run); the
             // row's cursor moves on by this tile's count right away
             seg_off[b] = gcur[b] - run;
