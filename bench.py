@@ -45,7 +45,7 @@ PHOTON_BINS = (0.01, 1e5)
 GAMMA_BINS = (1e-2, 1e3, 200)
 CONSTS = (1.0, 1.0, 1.0)  # B0, g_syn, e_syn_at_g_syn
 SEED = 123
-CPU_SAMPLE = 1_000_000  # particles per CPU-baseline step (x 200 bins = 2e8 evals)
+CPU_SAMPLE = 10_000_000  # particles per CPU-baseline step (x 200 bins = 2e9 evals, ~10 s on 16 cores)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload, from the
 # committed `ncu --set full` capture profiles/r1_ncu_full_v4_summary.json (not measurable
 # live: a number printed under a profiler is never a bench value)
