@@ -204,7 +204,7 @@ def run_reference(args) -> None:
                          "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # -------------------------------------------------------------------- our arm
@@ -455,10 +455,33 @@ def run_ours(args) -> None:
         "cpu_baseline": cpu_baseline,
         "other_configs": other,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout() -> None:
+    """Everything any library prints to fd 1 (NCCL's version banner, the reference's
+    py::print) goes to stderr; only emit() writes to the real stdout: ONE JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 
 def main() -> None:
@@ -478,6 +501,7 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
     PHOTON_BINS = (args.bins_lo, args.bins_hi)
     if args.impl == "reference":
         run_reference(args)
