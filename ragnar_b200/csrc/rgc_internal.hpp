@@ -134,8 +134,8 @@ namespace rgc {
   // adds the chunk's per-bin sums into d_acc[bins[s]] on the device (stream-ordered)
   int  run_spectrum_pair(const rgc_particles* prtls, std::size_t n, float B0, float g_syn,
                          float e_at, const TablePlan& tp, const float* bins_e_syn,
-                         const std::vector<int>& bins, double* d_acc, float* main_ms,
-                         bool defer_sync);
+                         const std::vector<int>& bins, double* d_acc, int* d_poison,
+                         float* main_ms, bool defer_sync);
   // after the caller's own stream synchronisation: kernel times of a deferred pass
   int  collect_pair_times(float* main_ms);
   bool pair_single_pass(std::size_t n); // n particles fit one pipeline pass

@@ -104,6 +104,7 @@ namespace rgc {
     int*        tot;    // [nbp] valid particles per bucket
     float2*     sorted; // (fc, w) in global bucket order, every bucket padded to an even length
     float2*     piece_mom; // [piece] {S0, S1} of the piece (float sums of <= kPieceLen terms)
+    int*        poison;    // != 0: a particle's chiR overflows float (see pair_prologue)
     double*     partials;  // [cta][nslots] hinge sums
     int         nslots;
     // shared-memory layout of the pair kernel (byte offsets, computed once on the host)
@@ -184,9 +185,14 @@ namespace rgc {
   //     coordinate by ~1e-6 cell;
   //   * sqrt, quotients and log10 go through rsqrt_nr / log2_pos (error < 1e-12).
   // The weight chiR is rounded to float exactly as in the reference.
+  // Returns true with (bucket, fc, w), false for a particle the reference skips.  A
+  // particle that poisons the reference's result raises *P.poison (rare path): chiR =
+  // real_t(sqrt(q) / B0) = +inf makes e_peak = +inf > 0, x0 = e_syn / e_peak = 0 < xmin,
+  // F = yfill = 0 and the term e_syn * inf * 0 = NaN in EVERY photon bin
+  // (synchrotron.hpp:162-171).
   __device__ __forceinline__ bool pair_prologue(const PairParams& P, float ux, float uy, float uz,
-                                                float ex, float ey, float ez, float bx, float by,
-                                                float bz, unsigned& bucket, float& fc, float& w) {
+                                               float ex, float ey, float ez, float bx, float by,
+                                               float bz, unsigned& bucket, float& fc, float& w) {
     const double dux = (double)ux, duy = (double)uy, duz = (double)uz;
     const double dex = (double)ex, dey = (double)ey, dez = (double)ez;
     const double dbx = (double)bx, dby = (double)by, dbz = (double)bz;
@@ -200,10 +206,18 @@ namespace rgc {
     const double q   = fma(-bde, bde, fma(sz, sz, fma(sy, sy, sx * sx)));
     // q <= 0: chiR = 0 or NaN in the reference, the pair is skipped (synchrotron.hpp:162);
     // NaN / inf inputs fail this or the range checks below
-    if (!(q > 1e-280 && q < 1e280)) {
+    if (!(q > 1e-280)) {
       return false;
     }
+    // (q = +inf gives chi = NaN here: 1/sqrt(inf) = 0, inf * 0)
     const double chi = (q * rsqrt_nr(q)) * P.inv_B0;
+    if (!(chi <= 3.4028235677973366e38)) { // chiR rounds to +inf as a float, or q is huge / inf
+      const double chi_big = sqrt(q) * P.inv_B0;
+      if (chi_big > 3.4028235677973366e38 && P.e_scale * g2 > 0.0) {
+        atomicAdd(P.poison, 1);
+      }
+      return false;
+    }
     const double ep  = (P.e_scale * g2) * chi;
     // float(e_peak) must be a positive finite float (else x0 = e_syn / e_peak is
     // off the table on either side)
@@ -763,7 +777,10 @@ namespace rgc {
           issue(s);
         }
       }
-      float fap[GPW], sgn[GPW], ds[GPW], s2[GPW];
+      // s2: float sums of up to 256 entries, folded into the piece's sums s2p: short float
+      // chains keep the rounding drift of long runs of (nearly) identical addends — a
+      // mono-energetic population — at the 1e-6 level
+      float fap[GPW], sgn[GPW], ds[GPW], s2[GPW], s2p[GPW];
 #pragma unroll
       for (int g = 0; g < GPW; ++g) {
         const float4 dh = coef[max(aoff[g] + b, 0)];
@@ -771,6 +788,7 @@ namespace rgc {
         sgn[g] = dh.z;
         fap[g] = (fa0[g] - dh.y) * dh.z;
         s2[g]  = 0.0f;
+        s2p[g] = 0.0f;
       }
 #define RGC_PAIR_ONE(FC, W)                                                         \
   {                                                                                 \
@@ -822,18 +840,25 @@ namespace rgc {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           issue(s + kStages);
         }
+        if ((s & 3) == 3 || s + 1 == nst) { // every 256 entries
+#pragma unroll
+          for (int g = 0; g < GPW; ++g) {
+            s2p[g] += s2[g];
+            s2[g] = 0.0f;
+          }
+        }
       }
 #undef RGC_PAIR_BODY
 #undef RGC_PAIR_ONE
       tstage += (unsigned)nst;
 #pragma unroll
       for (int g = 0; g < GPW; ++g) {
-        accd[g] = fma((double)ds[g], (double)s2[g], accd[g]);
+        accd[g] = fma((double)ds[g], (double)s2p[g], accd[g]);
       }
       if (col == 0 && lane >= 30) {
         // spare lanes 30 / 31 of the last group carry S0 / S1 of this piece
         float* pm = reinterpret_cast<float*>(P.piece_mom + piece);
-        pm[lane - 30] = s2[GPW - 1];
+        pm[lane - 30] = s2p[GPW - 1];
       }
     }
 
@@ -1151,11 +1176,12 @@ namespace rgc {
   }
 
   // One pipeline pass per <= 2^27 particles over one chunk of bins.
-  // d_acc[bins[s]] += sum_i w_i F_is (before the e_syn factor), on the device.
+  // d_acc[bins[s]] += sum_i w_i F_is (before the e_syn factor), on the device;
+  // *d_poison is raised when a particle's chiR overflows float (see pair_prologue).
   int run_spectrum_pair(const rgc_particles_t* prtls, std::size_t n, float B0, float g_syn,
                         float e_at, const TablePlan& tp, const float* bins_e_syn,
-                        const std::vector<int>& bins, double* d_acc, float* main_ms,
-                        bool defer_sync) {
+                        const std::vector<int>& bins, double* d_acc, int* d_poison,
+                        float* main_ms, bool defer_sync) {
     auto&             c  = ctx();
     const CachedPlan* cp = nullptr;
     RGC_TRY(cached_pair_plan(tp, bins_e_syn, bins, &cp));
@@ -1229,6 +1255,7 @@ namespace rgc {
     P.keys      = reinterpret_cast<unsigned short*>(sb + off_keys);
     P.counts    = reinterpret_cast<int*>(sb + off_cnt);
     P.tot       = reinterpret_cast<int*>(sb + off_tot);
+    P.poison    = d_poison;
     P.sorted    = reinterpret_cast<float2*>(sb + off_sort);
     P.piece_mom = reinterpret_cast<float2*>(sb + off_mom);
     P.partials  = reinterpret_cast<double*>(sb + off_part);

@@ -83,6 +83,7 @@ namespace rgc {
     // output: partials[cta][ngroups * 32]
     double* partials;
     int     nbins_pad;
+    int*    poison; // raised when a particle's chiR is +inf (every bin becomes NaN)
   };
 
   __device__ __forceinline__ int2 particle_prologue(const SpectrumParams& P, float ux,
@@ -105,7 +106,11 @@ namespace rgc {
       (float)((((double)P.e_at * gamma) * gamma) * (double)chiR / (double)(P.g_syn * P.g_syn));
     int2 out = make_int2(0, 0);
     // reference synchrotron.hpp:162 `if (e_peak > 0.0)`; +inf passes there but
-    // gives x0 = 0 < xmin, i.e. nothing
+    // gives x0 = 0 < xmin, i.e. F = yfill = 0: nothing for a finite chiR, and the term
+    // e_syn * inf * 0 = NaN in every bin for chiR = +inf
+    if (chiR == __int_as_float(0x7f800000) && e_peak == __int_as_float(0x7f800000)) {
+      atomicAdd(P.poison, 1);
+    }
     if (e_peak > 0.0f && e_peak < __int_as_float(0x7f800000)) {
       const double c = P.c0 - log10((double)e_peak) * P.inv_dL;
       if (c >= P.c_lo && c < P.c_hi) {
@@ -307,6 +312,15 @@ namespace rgc {
     }
   }
 
+  // a poisoned population: every bin becomes NaN, as in the reference
+  __global__ void poison_all_kernel(const int* __restrict__ poison, int nbins,
+                                    double* __restrict__ d_acc) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nbins && *poison != 0) {
+      d_acc[j] = __longlong_as_double(0x7ff8000000000000ll);
+    }
+  }
+
   int launch_scatter_add(const double* src, const int* binmap, int nslots, double* d_acc) {
     scatter_add_kernel<<<(nslots + 127) / 128, 128, 0, ctx().stream>>>(src, binmap, nslots, d_acc);
     RGC_CUDA(cudaGetLastError());
@@ -496,10 +510,11 @@ namespace rgc {
     // per-bin sums are accumulated on the device (one small buffer that survives the
     // scratch re-layouts of the launches), all-reduced once and read back once
     void* result = nullptr;
-    RGC_TRY(ensure_result(nbins * sizeof(double), &result));
-    double* d_acc = static_cast<double*>(result);
+    RGC_TRY(ensure_result(nbins * sizeof(double) + 16, &result));
+    double* d_acc    = static_cast<double*>(result);
+    int*    d_poison = reinterpret_cast<int*>(d_acc + nbins);
     RGC_CUDA(cudaEventRecord(c.ev[0], c.stream));
-    RGC_CUDA(cudaMemsetAsync(d_acc, 0, nbins * sizeof(double), c.stream));
+    RGC_CUDA(cudaMemsetAsync(d_acc, 0, nbins * sizeof(double) + 16, c.stream));
     float main_ms  = 0.f;
     bool  deferred = false;
     // ---- bucketed hinge path (rgc_sync_pair.cu) for every chunk it can take;
@@ -520,7 +535,7 @@ namespace rgc {
       for (auto& chunk : chunks) {
         if (allow && pair_path_eligible(tp, bins_e_syn, chunk)) {
           RGC_TRY(run_spectrum_pair(src.prtls, src.n, src.B0, src.g_syn, src.e_at, tp, bins_e_syn,
-                                    chunk, d_acc, &main_ms, deferred));
+                                    chunk, d_acc, d_poison, &main_ms, deferred));
         } else {
           rest.push_back(std::move(chunk));
         }
@@ -587,6 +602,7 @@ namespace rgc {
       P.c_hi      = lp.c_hi;
       P.partials  = d_part;
       P.nbins_pad = lp.ngroups * 32;
+      P.poison    = d_poison;
       const std::size_t smem = (std::size_t)lp.n_pad * sizeof(float2) +
                                std::max<std::size_t>((std::size_t)(kTile + 2 * kWarps) * sizeof(int2),
                                                      (std::size_t)kWarps * lp.gpw * 32 * sizeof(double));
@@ -611,6 +627,12 @@ namespace rgc {
       float ms = 0.f;
       RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]));
       main_ms += ms;
+    }
+    if (!from_dist) {
+      poison_all_kernel<<<(unsigned)((nbins + 127) / 128), 128, 0, c.stream>>>(d_poison, (int)nbins,
+                                                                               d_acc);
+      RGC_CUDA(cudaGetLastError());
+      count_launch(1);
     }
     if (allreduce) {
       RGC_TRY(allreduce_sum_f64(d_acc, nbins));

@@ -237,3 +237,19 @@ def test_spectrum_multi_pass(cabi, port, monkeypatch):
     assert np.max(np.abs(many[big] - want[big]) / want[big]) < SPEC_RTOL
     assert np.max(np.abs(many[big] - one[big]) / one[big]) < 1e-6
     assert np.array_equal(many == 0, want == 0)
+
+
+def test_spectrum_infinite_field_poisons_every_bin(cabi, port):
+    """chiR = +inf (an infinite field component): the reference's term is e_syn * inf * F(0)
+    = inf * 0 = NaN in every bin (synchrotron.hpp:162-171); NaN inputs are skipped"""
+    U, E, B = synth.full3d(5000, seed=8)
+    bins = cabi.logspace(0.01, 1e5, 200)
+    B[1][123] = np.inf
+    got = cabi.sync_spectrum_particles(_particles(cabi, U, E, B), bins, 1.0, 1.0, 1.0)[1]
+    _, want = port.sync_spectrum_particles(U, E, B, bins, 1.0, 1.0, 1.0)
+    assert np.all(np.isnan(want)) and np.all(np.isnan(got))
+    B[1][123] = np.nan  # NaN chiR fails `e_peak > 0`: that particle is skipped
+    U[0][7] = np.inf    # beta = inf / inf = NaN: skipped as well
+    got = cabi.sync_spectrum_particles(_particles(cabi, U, E, B), bins, 1.0, 1.0, 1.0)[1]
+    _, want = port.sync_spectrum_particles(U, E, B, bins, 1.0, 1.0, 1.0)
+    assert np.all(np.isfinite(want)) and synth.rel_err(got, want) < SPEC_RTOL
