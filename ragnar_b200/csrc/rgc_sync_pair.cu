@@ -174,17 +174,19 @@ namespace rgc {
     return (double)ex + fma(sc, t, sc);
   }
 
+  // x rounded to float precision (24 significant bits, nearest) without leaving the
+  // fp64 pipe: Veltkamp's split with 2^29 + 1.  Equal to (double)(float)x for normal
+  // floats; saves the two XU-pipe conversions (16 lanes/clk/SM against 64 for fp64).
+  __device__ __forceinline__ double round24(double x) {
+    const double t = x * 536870913.0;
+    return t - (t - x);
+  }
+
   // reference src/physics/synchrotron.hpp:193-231 — gamma, beta, beta.E, beta x B,
   // chiR, e_peak — in fp64 like the reference's promoted arithmetic, then the table
-  // coordinate of e_peak split into bucket and fraction.  Two deliberate, bounded
-  // departures from the reference's rounding sequence (the gather kernel keeps the
-  // exact one; tests pin the two paths against each other):
-  //   * ux*ux etc. enter gamma^2 unrounded (the reference rounds each square to float
-  //     before promoting it), and e_peak is formed from the unrounded chiR and is not
-  //     itself rounded to float: e_peak moves by < 2 float ulp, i.e. the table
-  //     coordinate by ~1e-6 cell;
-  //   * sqrt, quotients and log10 go through rsqrt_nr / log2_pos (error < 1e-12).
-  // The weight chiR is rounded to float exactly as in the reference.
+  // coordinate of e_peak split into bucket and fraction.  The float roundings of the
+  // reference's sequence are kept (squares of U, chiR, e_peak); sqrt, quotients and
+  // log10 go through rsqrt_nr / log2_pos (relative error < 1e-12, far below a float ulp).
   // Returns true with (bucket, fc, w), false for a particle the reference skips.  A
   // particle that poisons the reference's result raises *P.poison (rare path): chiR =
   // real_t(sqrt(q) / B0) = +inf makes e_peak = +inf > 0, x0 = e_syn / e_peak = 0 < xmin,
@@ -196,7 +198,9 @@ namespace rgc {
     const double dux = (double)ux, duy = (double)uy, duz = (double)uz;
     const double dex = (double)ex, dey = (double)ey, dez = (double)ez;
     const double dbx = (double)bx, dby = (double)by, dbz = (double)bz;
-    const double g2  = fma(duz, duz, fma(duy, duy, fma(dux, dux, 1.0)));
+    // gamma^2 from the float squares, like `1.0 + ux * ux + uy * uy + uz * uz` in the
+    // reference (each square rounded to float, then promoted)
+    const double g2 = ((1.0 + round24(dux * dux)) + round24(duy * duy)) + round24(duz * duz);
     const double rg  = rsqrt_nr(g2);
     const double beta_x = dux * rg, beta_y = duy * rg, beta_z = duz * rg;
     const double bde = fma(beta_z, dez, fma(beta_y, dey, beta_x * dex));
@@ -218,13 +222,18 @@ namespace rgc {
       }
       return false;
     }
-    const double ep  = (P.e_scale * g2) * chi;
+    // chiR and e_peak are rounded to float exactly where the reference rounds them
+    // (synchrotron.hpp:230-231): a mono-energetic population has no other particles to
+    // average a half-ulp coordinate shift away
+    const float  chi_f = (float)chi; // the weight; off the critical path
+    const double ep_d  = (P.e_scale * g2) * round24(chi);
     // float(e_peak) must be a positive finite float (else x0 = e_syn / e_peak is
     // off the table on either side)
-    if (!(ep > 1e-37 && ep < 3.4028234e38)) {
+    if (!(ep_d > 1e-37 && ep_d < 3.4028234e38)) {
       return false;
     }
-    const double c = fma(-log2_pos(ep), P.cells_per_octave, P.c0);
+    const double ep = round24(ep_d);
+    const double c  = fma(-log2_pos(ep), P.cells_per_octave, P.c0);
     if (!(c >= P.c_lo && c < P.c_hi)) {
       return false;
     }
@@ -241,7 +250,7 @@ namespace rgc {
     }
     bucket = (unsigned)(ri - P.kmin);
     fc     = (float)(c - fl);
-    w      = (float)chi;
+    w      = chi_f;
     return true;
   }
 
@@ -778,8 +787,9 @@ namespace rgc {
         }
       }
       // s2: float sums of up to 256 entries, folded into the piece's sums s2p: short float
-      // chains keep the rounding drift of long runs of (nearly) identical addends — a
-      // mono-energetic population — at the 1e-6 level
+      // chains bound the rounding drift of long runs of identical addends (a mono-energetic
+      // population, where the drift is one-sided and the same in every piece) to ~1e-5;
+      // folding every 64 entries would give 3e-6 for 5 % of this kernel's time
       float fap[GPW], sgn[GPW], ds[GPW], s2[GPW], s2p[GPW];
 #pragma unroll
       for (int g = 0; g < GPW; ++g) {
@@ -1201,6 +1211,8 @@ namespace rgc {
     const char* sr          = std::getenv("RGC_SORT_RANK"); // "ballot": guaranteed-order ranking
     const bool  atomic_rank = !(sr && std::strcmp(sr, "ballot") == 0);
     const int sort_ctas_per_sm = 2;
+    const char* pm       = std::getenv("RGC_PROLOGUE_MINB"); // tuning knob: prologue CTAs per SM
+    const int   pro_minb = (pm && std::atoi(pm) == 4) ? 4 : 3;
     struct Geom {
       int ntiles, rows, tiles_per_row, ctas1, tiles_per_cta1;
     };
@@ -1210,7 +1222,7 @@ namespace rgc {
       g.rows           = std::max(1, std::min(c.sm_count * sort_ctas_per_sm, g.ntiles));
       g.tiles_per_row  = (g.ntiles + g.rows - 1) / g.rows;
       g.rows           = (g.ntiles + g.tiles_per_row - 1) / g.tiles_per_row;
-      g.ctas1          = std::max(1, std::min(c.sm_count * 3, g.ntiles));
+      g.ctas1          = std::max(1, std::min(c.sm_count * pro_minb, g.ntiles));
       g.tiles_per_cta1 = (g.ntiles + g.ctas1 - 1) / g.ctas1;
       g.ctas1          = (g.ntiles + g.tiles_per_cta1 - 1) / g.tiles_per_cta1;
       return g;
@@ -1265,8 +1277,6 @@ namespace rgc {
     double* d_msum = reinterpret_cast<double*>(sb + off_msum);
     double* d_out  = reinterpret_cast<double*>(sb + off_out);
     float               pro_ms = 0.f, sort_ms = 0.f;
-    const char*         pm       = std::getenv("RGC_PROLOGUE_MINB"); // tuning knob
-    const int           pro_minb = pm ? std::atoi(pm) : 3;
     const std::size_t   sort_smem = sort_smem_layout(pp.nbp).total;
     RGC_CUDA(cudaFuncSetAttribute(sync_sort_kernel<true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));

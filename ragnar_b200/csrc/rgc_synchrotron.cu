@@ -312,6 +312,43 @@ namespace rgc {
     }
   }
 
+  // ---- SynchrotronSpectrumFromDist (reference synchrotron.hpp:72-95): G x M pairs, at
+  // most a few million — latency-bound, so it is evaluated in fp64 with full-precision
+  // table coordinates (the fixed-point gather kernel resolves 1e-6 cell, which shows at
+  // the 1e-5 level next to the zeros of F when only a few hundred terms are summed).
+  // One thread per photon bin, the distribution staged in shared memory in chunks,
+  // terms added in distribution order: deterministic.
+  //   t = a_j + c_g,  F = v_k + s_k (t - k) in cell k = floor(t), 0 outside [0, T-1)
+  __global__ void __launch_bounds__(128)
+    sync_dist_kernel(const double* __restrict__ a, int nbins, const double2* __restrict__ cw, int ndist,
+                     const double2* __restrict__ coef_vs, int T, double* __restrict__ out) {
+    __shared__ double2 scw[256];
+    const int j  = blockIdx.x * blockDim.x + threadIdx.x;
+    const double aj = j < nbins ? a[j] : 0.0;
+    double acc = 0.0;
+    for (int g0 = 0; g0 < ndist; g0 += 256) {
+      const int cnt = min(256, ndist - g0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        scw[i] = cw[g0 + i];
+      }
+      __syncthreads();
+      if (j < nbins) {
+        for (int i = 0; i < cnt; ++i) {
+          const double t = aj + scw[i].x;
+          if (t >= 0.0 && t < (double)(T - 1)) { // x0 in [xmin, xmax); NaN coordinates fail
+            const double  k  = floor(t);
+            const double2 vs = coef_vs[(int)k];
+            acc = fma(scw[i].y, fma(vs.y, t - k, vs.x), acc);
+          }
+        }
+      }
+    }
+    if (j < nbins) {
+      out[j] = acc;
+    }
+  }
+
   // a poisoned population: every bin becomes NaN, as in the reference
   __global__ void poison_all_kernel(const int* __restrict__ poison, int nbins,
                                     double* __restrict__ d_acc) {
@@ -701,64 +738,74 @@ extern "C" {
                              const float* tab_x, const float* tab_y, size_t tab_n, float g_syn,
                              float e_syn_at_g_syn, float* out_spec, double* out_spec64) {
     RGC_REQUIRE_INIT();
-    // Per-distribution-bin prologue on the host (ndist values): the table
-    // coordinate needs the launch plan, so only (e_peak, weight) are formed here
-    // and converted per launch below.  reference synchrotron.hpp:78-79,90,92.
+    if (nbins == 0) {
+      return RGC_OK;
+    }
+    if (ndist > (std::size_t)1 << 30 || nbins > (std::size_t)1 << 30) {
+      return fail(RGC_ERR_INVALID, "SynchrotronSpectrumFromDist: grid too large");
+    }
+    auto& c = ctx();
     TablePlan tp;
     RGC_TRY(make_table_plan(tab_x, tab_y, tab_n, tp));
-    std::vector<float> e_peak(ndist), weight(ndist);
+    const int T = (int)tp.T;
+    // per cell k: value of the cell's line at t = k and its slope (the reference's
+    // interpolant between the ACTUAL nodes tx[k], tx[k+1]: tabulation.hpp:39-41)
+    std::vector<double2> vs(T);
+    for (int k = 0; k + 1 < T; ++k) {
+      const double sk = (tp.y[k + 1] - tp.y[k]) / (tp.tx[k + 1] - tp.tx[k]);
+      vs[k]           = make_double2(tp.y[k] + sk * ((double)k - tp.tx[k]), sk);
+    }
+    vs[T - 1] = make_double2(0.0, 0.0);
+    // per distribution bin, on the host (ndist values): e_peak and the weight exactly as
+    // the reference forms them in float (synchrotron.hpp:78-79,90,92)
+    std::vector<double2> cw(ndist);
     for (std::size_t g = 0; g < ndist; ++g) {
-      const float gb = gbeta[g];
-      e_peak[g]      = e_syn_at_g_syn * gb * gb / (g_syn * g_syn);
-      weight[g]      = islog_bins_prtls ? f[g] * gb : f[g];
-    }
-    // The fixed-point particle coordinate depends on the launch's bin chunk;
-    // FromDist always fits one chunk in practice, but handle several.
-    std::vector<std::vector<int>> chunks;
-    std::vector<int>              nan_bins;
-    chunk_bins(tp, bins_e_syn, nbins, chunks, nan_bins);
-    std::vector<double> acc_total(nbins, 0.0);
-    float               ms_total[2] = { 0.f, 0.f };
-    for (auto& chunk : chunks) {
-      LaunchPlan lp;
-      RGC_TRY(make_launch_plan(tp, bins_e_syn, chunk, lp));
-      std::vector<int2> cw(ndist);
-      for (std::size_t g = 0; g < ndist; ++g) {
-        cw[g] = make_int2(0, 0);
-        if (e_peak[g] > 0.0f && std::isfinite(e_peak[g])) {
-          const double cc = lp.c0 - std::log10((double)e_peak[g]) / tp.dL;
-          if (cc >= lp.c_lo && cc < lp.c_hi) {
-            cw[g].x = (int)(unsigned)std::llrint(cc * (double)(1u << kFracBits));
-            std::memcpy(&cw[g].y, &weight[g], 4);
-          }
-        }
-      }
-      rgc_buf_t* cwbuf = nullptr;
-      RGC_TRY(rgc_buf_from_host(RGC_F64, cw.data(), ndist, &cwbuf)); // 8-byte elements
-      std::vector<float> sub_bins(chunk.size());
-      for (std::size_t s = 0; s < chunk.size(); ++s) {
-        sub_bins[s] = bins_e_syn[chunk[s]];
-      }
-      SpectrumSource src;
-      src.cw_dev = static_cast<const int2*>(cwbuf->dev);
-      src.n      = ndist;
-      std::vector<double> acc;
-      int rc = run_spectrum(src, true, sub_bins.data(), sub_bins.size(), tab_x, tab_y, tab_n,
-                            false, acc);
-      rgc_buf_release(cwbuf);
-      RGC_TRY(rc);
-      ms_total[0] += ctx().last_ms[0];
-      ms_total[1] += ctx().last_ms[1];
-      for (std::size_t s = 0; s < chunk.size(); ++s) {
-        acc_total[chunk[s]] = acc[s];
+      const float gb     = gbeta[g];
+      const float e_peak = e_syn_at_g_syn * gb * gb / (g_syn * g_syn);
+      const float weight = islog_bins_prtls ? f[g] * gb : f[g];
+      cw[g]              = make_double2(std::nan(""), 0.0); // NaN coordinate: contributes nothing
+      if (e_peak > 0.0f && std::isfinite(e_peak)) {
+        cw[g] = make_double2(-std::log10((double)e_peak) / tp.dL, (double)weight);
       }
     }
-    ctx().last_ms[0] = ms_total[0];
-    ctx().last_ms[1] = ms_total[1];
-    for (int j : nan_bins) {
-      acc_total[j] = std::nan("");
+    std::vector<double> a(nbins);
+    for (std::size_t j = 0; j < nbins; ++j) {
+      const float e = bins_e_syn[j];
+      a[j] = (e > 0.0f && std::isfinite(e)) ? (std::log10((double)e) - tp.L0) / tp.dL : std::nan("");
     }
-    finish_spectrum(acc_total, bins_e_syn, nbins, out_spec, out_spec64);
+    auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
+    const std::size_t o_a   = 0;
+    const std::size_t o_cw  = align(o_a + nbins * sizeof(double));
+    const std::size_t o_vs  = align(o_cw + ndist * sizeof(double2));
+    const std::size_t o_out = align(o_vs + (std::size_t)T * sizeof(double2));
+    void*             scratch = nullptr;
+    RGC_TRY(ensure_scratch(o_out + nbins * sizeof(double), &scratch));
+    char* sb = static_cast<char*>(scratch);
+    RGC_CUDA(cudaEventRecord(c.ev[0], c.stream));
+    RGC_TRY(copy_h2d(sb + o_a, a.data(), nbins * sizeof(double), c.stream));
+    RGC_TRY(copy_h2d(sb + o_cw, cw.data(), ndist * sizeof(double2), c.stream));
+    RGC_TRY(copy_h2d(sb + o_vs, vs.data(), (std::size_t)T * sizeof(double2), c.stream));
+    RGC_CUDA(cudaEventRecord(c.ev[2], c.stream));
+    sync_dist_kernel<<<(unsigned)((nbins + 127) / 128), 128, 0, c.stream>>>(
+      reinterpret_cast<const double*>(sb + o_a), (int)nbins,
+      reinterpret_cast<const double2*>(sb + o_cw), (int)ndist,
+      reinterpret_cast<const double2*>(sb + o_vs), T, reinterpret_cast<double*>(sb + o_out));
+    RGC_CUDA(cudaGetLastError());
+    count_launch(1);
+    RGC_CUDA(cudaEventRecord(c.ev[3], c.stream));
+    std::vector<double> acc(nbins);
+    RGC_CUDA(cudaMemcpyAsync(acc.data(), sb + o_out, nbins * sizeof(double), cudaMemcpyDeviceToHost,
+                             c.stream));
+    RGC_CUDA(cudaEventRecord(c.ev[1], c.stream));
+    RGC_CUDA(cudaStreamSynchronize(c.stream));
+    RGC_CUDA(cudaEventElapsedTime(&c.last_ms[0], c.ev[0], c.ev[1]));
+    RGC_CUDA(cudaEventElapsedTime(&c.last_ms[1], c.ev[2], c.ev[3]));
+    for (std::size_t j = 0; j < nbins; ++j) {
+      if (std::isnan(bins_e_syn[j])) {
+        acc[j] = std::nan(""); // as in the particle path; e <= 0 gives 0, +inf gives inf * 0
+      }
+    }
+    finish_spectrum(acc, bins_e_syn, nbins, out_spec, out_spec64);
     return RGC_OK;
   }
 
