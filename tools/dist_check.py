@@ -65,6 +65,39 @@ if rank == 0:
     print(f"[dist_check] world={world} n={n}: spectrum rel err vs oracle {err:.2e}, "
           f"weighted hist {herr:.2e}, counts bit-exact={np.array_equal(counts, want_c)}, "
           f"sharded vs one-rank spectrum {add:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
+# ---- the batched driver with sharded range reads (ragnar_b200/pipeline.py)
+import shutil
+import tempfile
+
+from ragnar_b200 import pipeline
+
+root = Path(tempfile.gettempdir()) / "rgc_dist_check_pipeline"
+if rank == 0:
+    shutil.rmtree(root, ignore_errors=True)
+    (root / "output" / "prtl").mkdir(parents=True)
+    m = 200_003
+    cabi.tristan_write_species(str(root), 7, 1, [c[:m] for q in (U, E, B) for c in q], with_coords=False,
+                               append=False)
+dist.barrier()
+m = 200_003
+rep = pipeline.process_steps(str(root), [7], [("e-", 1)], bins, gbins, *consts, rank=rank, world=world)
+if rank == 0:
+    r = rep.results[0]
+    _, want_p = oracle.port.sync_spectrum_particles([u[:m] for u in U], [e[:m] for e in E], [b[:m] for b in B],
+                                                    bins, *consts)
+    bigp = want_p >= 1e-6 * want_p.max()
+    perr = float(np.max(np.abs(r.spectrum64[bigp] - want_p[bigp]) / want_p[bigp]))
+    _, want_ph, _ = oracle.port.energy_distribution(*[u[:m] for u in U], gbins, True, True)
+    nzp = want_ph > 0
+    pherr = float(np.max(np.abs(r.distribution[nzp] - want_ph[nzp]) / want_ph[nzp]))
+    lo_r, cnt_r = rdist.shard_range(m, rank, world)
+    okp = perr < 1e-5 and pherr < 1e-5 and r.nparticles == cnt_r
+    ok = ok and okp
+    print(f"[dist_check] world={world} pipeline (sharded reads of {m} particles): spectrum rel err {perr:.2e}, "
+          f"distribution {pherr:.2e}, rank-0 share {r.nparticles} -> {'OK' if okp else 'FAIL'}", flush=True)
+dist.barrier()
+if rank == 0:
+    shutil.rmtree(root, ignore_errors=True)
 flag = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(flag)
 dist.barrier()
