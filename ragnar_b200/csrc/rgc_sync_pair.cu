@@ -80,7 +80,15 @@ namespace rgc {
   constexpr int kStageLen    = 64;   // sorted entries per TMA stage (512 B)
   constexpr int kStages      = 4;    // ring depth per warp
 
+  // fp64 constants of the prologue, read as constant-bank operands (an immediate double
+  // whose low word is not zero costs two UMOVs per use otherwise)
+  struct PairConsts {
+    double sqrt2, k15, k13, k11, k9, k7, k5, k3, two_over_ln2, split24, magic, flt_max, ep_lo, ep_hi,
+      q_lo;
+  };
+
   struct PairParams {
+    PairConsts   kc;
     const float* u[3];
     const float* e[3];
     const float* b[3];
@@ -146,14 +154,14 @@ namespace rgc {
     return fma(r * 0.5, e, r);
   }
 
-  // log2 of a positive normal double, |error| < 1e-12: exponent + atanh series of
+  // log2 of a positive normal double, |error| < 3e-11: exponent + atanh series of
   // the mantissa folded into [sqrt(1/2), sqrt(2)); the quotient (m-1)/(m+1) comes
   // from a MUFU.RCP64H seed refined by one Newton step
-  __device__ __forceinline__ double log2_pos(double x) {
+  __device__ __forceinline__ double log2_pos(const PairConsts& K, double x) {
     const int hi = __double2hiint(x);
     int       ex = ((hi >> 20) & 0x7ff) - 1023;
     double    m  = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
-    if (m > 1.4142135623730951) {
+    if (m > K.sqrt2) {
       m *= 0.5;
       ex += 1;
     }
@@ -163,22 +171,21 @@ namespace rgc {
     rc              = fma(rc, fma(-b, rc, 1.0), rc);
     const double s  = a * rc;
     const double s2 = s * s; // <= 0.0295
-    double       t  = fma(s2, 1.0 / 15.0, 1.0 / 13.0);
-    t               = fma(s2, t, 1.0 / 11.0);
-    t               = fma(s2, t, 1.0 / 9.0);
-    t               = fma(s2, t, 1.0 / 7.0);
-    t               = fma(s2, t, 1.0 / 5.0);
-    t               = fma(s2, t, 1.0 / 3.0);
+    double       t  = fma(s2, K.k11, K.k9); // next term s^13/13 <= 2.5e-11 in log2
+
+    t               = fma(s2, t, K.k7);
+    t               = fma(s2, t, K.k5);
+    t               = fma(s2, t, K.k3);
     t               = t * s2;
-    const double sc = s * 2.8853900817779268; // 2 / ln 2
+    const double sc = s * K.two_over_ln2; // 2 / ln 2
     return (double)ex + fma(sc, t, sc);
   }
 
   // x rounded to float precision (24 significant bits, nearest) without leaving the
   // fp64 pipe: Veltkamp's split with 2^29 + 1.  Equal to (double)(float)x for normal
   // floats; saves the two XU-pipe conversions (16 lanes/clk/SM against 64 for fp64).
-  __device__ __forceinline__ double round24(double x) {
-    const double t = x * 536870913.0;
+  __device__ __forceinline__ double round24(const PairConsts& K, double x) {
+    const double t = x * K.split24; // 2^29 + 1
     return t - (t - x);
   }
 
@@ -186,7 +193,7 @@ namespace rgc {
   // chiR, e_peak — in fp64 like the reference's promoted arithmetic, then the table
   // coordinate of e_peak split into bucket and fraction.  The float roundings of the
   // reference's sequence are kept (squares of U, chiR, e_peak); sqrt, quotients and
-  // log10 go through rsqrt_nr / log2_pos (relative error < 1e-12, far below a float ulp).
+  // log10 go through rsqrt_nr / log2_pos (error < 3e-11, i.e. 2e-10 cell: far below a float ulp).
   // Returns true with (bucket, fc, w), false for a particle the reference skips.  A
   // particle that poisons the reference's result raises *P.poison (rare path): chiR =
   // real_t(sqrt(q) / B0) = +inf makes e_peak = +inf > 0, x0 = e_syn / e_peak = 0 < xmin,
@@ -200,7 +207,8 @@ namespace rgc {
     const double dbx = (double)bx, dby = (double)by, dbz = (double)bz;
     // gamma^2 from the float squares, like `1.0 + ux * ux + uy * uy + uz * uz` in the
     // reference (each square rounded to float, then promoted)
-    const double g2 = ((1.0 + round24(dux * dux)) + round24(duy * duy)) + round24(duz * duz);
+    const PairConsts& K = P.kc;
+    const double g2 = ((1.0 + round24(K, dux * dux)) + round24(K, duy * duy)) + round24(K, duz * duz);
     const double rg  = rsqrt_nr(g2);
     const double beta_x = dux * rg, beta_y = duy * rg, beta_z = duz * rg;
     const double bde = fma(beta_z, dez, fma(beta_y, dey, beta_x * dex));
@@ -210,14 +218,14 @@ namespace rgc {
     const double q   = fma(-bde, bde, fma(sz, sz, fma(sy, sy, sx * sx)));
     // q <= 0: chiR = 0 or NaN in the reference, the pair is skipped (synchrotron.hpp:162);
     // NaN / inf inputs fail this or the range checks below
-    if (!(q > 1e-280)) {
+    if (!(q > K.q_lo)) {
       return false;
     }
     // (q = +inf gives chi = NaN here: 1/sqrt(inf) = 0, inf * 0)
     const double chi = (q * rsqrt_nr(q)) * P.inv_B0;
-    if (!(chi <= 3.4028235677973366e38)) { // chiR rounds to +inf as a float, or q is huge / inf
+    if (!(chi <= K.flt_max)) { // chiR rounds to +inf as a float, or q is huge / inf
       const double chi_big = sqrt(q) * P.inv_B0;
-      if (chi_big > 3.4028235677973366e38 && P.e_scale * g2 > 0.0) {
+      if (chi_big > K.flt_max && P.e_scale * g2 > 0.0) {
         atomicAdd(P.poison, 1);
       }
       return false;
@@ -226,21 +234,21 @@ namespace rgc {
     // (synchrotron.hpp:230-231): a mono-energetic population has no other particles to
     // average a half-ulp coordinate shift away
     const float  chi_f = (float)chi; // the weight; off the critical path
-    const double ep_d  = (P.e_scale * g2) * round24(chi);
+    const double ep_d  = (P.e_scale * g2) * round24(K, chi);
     // float(e_peak) must be a positive finite float (else x0 = e_syn / e_peak is
     // off the table on either side)
-    if (!(ep_d > 1e-37 && ep_d < 3.4028234e38)) {
+    if (!(ep_d > K.ep_lo && ep_d < K.ep_hi)) {
       return false;
     }
-    const double ep = round24(ep_d);
-    const double c  = fma(-log2_pos(ep), P.cells_per_octave, P.c0);
+    const double ep = round24(K, ep_d);
+    const double c  = fma(-log2_pos(K, ep), P.cells_per_octave, P.c0);
     if (!(c >= P.c_lo && c < P.c_hi)) {
       return false;
     }
     // floor(c) without FRND / F2I: round-to-nearest of c - 1/2 through the 2^52 trick;
     // an exact integer c may land on either neighbour, (K, fc = 0) and (K - 1, fc = 1)
     // being the same table coordinate
-    const double magic = 6755399441055744.0; // 1.5 * 2^52
+    const double magic = K.magic; // 1.5 * 2^52
     const double rm    = (c - 0.5) + magic;
     int          ri    = __double2loint(rm);
     double       fl    = rm - magic;
@@ -1247,6 +1255,9 @@ namespace rgc {
     RGC_TRY(ensure_scratch(total, &scratch));
     char* sb = static_cast<char*>(scratch);
     PairParams P {};
+    P.kc = PairConsts { 1.4142135623730951, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0,
+                        1.0 / 5.0, 1.0 / 3.0, 2.8853900817779268, 536870913.0, 6755399441055744.0,
+                        3.4028235677973366e38, 1e-37, 3.4028234e38, 1e-280 };
     P.slot_i   = reinterpret_cast<const int2*>(cp->dev + cp->off_si);
     P.slot_f   = reinterpret_cast<const float2*>(cp->dev + cp->off_sf);
     P.coef_dh  = reinterpret_cast<const float4*>(cp->dev + cp->off_dh);
