@@ -1,4 +1,9 @@
-// Synchrotron spectrum kernels for sm_100a.
+// Synchrotron spectrum entry points, the FromDist kernel and the gather fallback for
+// sm_100a.  (The main path of the particle spectrum is the bucketed hinge pipeline of
+// rgc_sync_pair.cu; run_spectrum below routes every eligible bin chunk to it and
+// keeps the gather kernel of this file for tables that do not vanish at both ends and
+// for bin sets spanning more than ~1000 table cells.  SynchrotronSpectrumFromDist is
+// the small fp64 kernel sync_dist_kernel.)
 //
 // Replaces (reference paths relative to haykh/ragnar @ fceb6b08):
 //   sync::Kernel<D>::operator() / OmegaSync_ChiR   src/physics/synchrotron.hpp:145-232
@@ -10,7 +15,7 @@
 //     x0 = e_syn[j] / e_peak_i;  F = loglog-table(x0);  spec[j] += e_syn[j] * chiR_i * F
 // with ~5 log10f + 5 divisions per pair and (chiR_i, e_peak_i) recomputed per bin.
 //
-// Device formulation (same numbers, different arithmetic):
+// Gather kernel (same numbers, different arithmetic):
 //   * the table is linear in t = (log10 x0 - log10 x[0]) / dL between its nodes,
 //     and t = a_j + c_i with a_j = (log10 e_syn[j] - log10 x[0]) / dL per bin and
 //     c_i = -log10(e_peak_i) / dL per particle.  Both are computed ONCE in fp64 and
@@ -59,12 +64,10 @@ namespace rgc {
   constexpr int      kMaxGroups = 64;  // 8 warp columns x 8 groups = 2048 bins per launch
 
   struct SpectrumParams {
-    // particle columns (FROM_DIST == false)
+    // particle columns
     const float* u[3];
     const float* e[3];
     const float* b[3];
-    // precomputed (c_fx, w) pairs (FROM_DIST == true)
-    const int2*  cw_in;
     std::size_t  nprtl;
     // per-bin fixed-point coordinates, padded to ngroups * 32
     const unsigned* a_fx;
@@ -121,7 +124,7 @@ namespace rgc {
     return out;
   }
 
-  template <int GPW, bool FROM_DIST>
+  template <int GPW>
   __global__ void __launch_bounds__(kThreads, 2)
     sync_spectrum_kernel(const __grid_constant__ SpectrumParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -167,29 +170,20 @@ namespace rgc {
         r[k] = make_int2(0, 0);
       }
       if (i0 < P.nprtl) {
-        if constexpr (FROM_DIST) {
+        float4 v[9];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (i0 + k < P.nprtl) {
-              r[k] = P.cw_in[i0 + k];
-            }
-          }
-        } else {
-          float4 v[9];
+        for (int d = 0; d < 3; ++d) {
+          v[d]     = *reinterpret_cast<const float4*>(P.u[d] + i0);
+          v[3 + d] = *reinterpret_cast<const float4*>(P.e[d] + i0);
+          v[6 + d] = *reinterpret_cast<const float4*>(P.b[d] + i0);
+        }
+        const float* f = reinterpret_cast<const float*>(v);
 #pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            v[d]     = *reinterpret_cast<const float4*>(P.u[d] + i0);
-            v[3 + d] = *reinterpret_cast<const float4*>(P.e[d] + i0);
-            v[6 + d] = *reinterpret_cast<const float4*>(P.b[d] + i0);
-          }
-          const float* f = reinterpret_cast<const float*>(v);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (i0 + k < P.nprtl) {
-              r[k] = particle_prologue(P, f[0 * 4 + k], f[1 * 4 + k], f[2 * 4 + k],
-                                       f[3 * 4 + k], f[4 * 4 + k], f[5 * 4 + k],
-                                       f[6 * 4 + k], f[7 * 4 + k], f[8 * 4 + k]);
-            }
+        for (int k = 0; k < 4; ++k) {
+          if (i0 + k < P.nprtl) {
+            r[k] = particle_prologue(P, f[0 * 4 + k], f[1 * 4 + k], f[2 * 4 + k],
+                                     f[3 * 4 + k], f[4 * 4 + k], f[5 * 4 + k],
+                                     f[6 * 4 + k], f[7 * 4 + k], f[8 * 4 + k]);
           }
         }
       }
@@ -453,13 +447,12 @@ namespace rgc {
     return RGC_OK;
   }
 
-  template <bool FROM_DIST>
   static void launch_spectrum(int gpw, dim3 grid, std::size_t smem, cudaStream_t st,
                               const SpectrumParams& P) {
     switch (gpw) {
 #define RGC_CASE(G)                                                                   \
   case G:                                                                             \
-    sync_spectrum_kernel<G, FROM_DIST><<<grid, kThreads, smem, st>>>(P);              \
+    sync_spectrum_kernel<G><<<grid, kThreads, smem, st>>>(P);                         \
     break;
       RGC_CASE(1)
       RGC_CASE(2)
@@ -526,14 +519,13 @@ namespace rgc {
 
   struct SpectrumSource {
     const rgc_particles_t* prtls { nullptr }; // particles path
-    const int2*            cw_dev { nullptr }; // dist path
     std::size_t            n { 0 };
     float                  B0 { 1 }, g_syn { 1 }, e_at { 1 };
   };
 
   // Runs all launches, leaves acc64[nbins] = sum_i w_i F_ij (before the e_syn factor)
   // on the device (all-reduced when requested) and copies it to the host.
-  static int run_spectrum(const SpectrumSource& src, bool from_dist, const float* bins_e_syn,
+  static int run_spectrum(const SpectrumSource& src, const float* bins_e_syn,
                           std::size_t nbins, const float* tab_x, const float* tab_y,
                           std::size_t tab_n, bool allreduce, std::vector<double>& acc_host) {
     auto& c = ctx();
@@ -556,10 +548,10 @@ namespace rgc {
     bool  deferred = false;
     // ---- bucketed hinge path (rgc_sync_pair.cu) for every chunk it can take;
     // RGC_SPECTRUM_PATH=gather forces the gather kernel below (A/B checks)
-    if (!from_dist && src.n == 0) {
+    if (src.n == 0) {
       chunks.clear(); // a rank without particles launches nothing but still joins the all-reduce
     }
-    if (!from_dist && src.n > 0) {
+    if (src.n > 0) {
       const char* force = std::getenv("RGC_SPECTRUM_PATH");
       const bool  allow = !(force && std::strcmp(force, "gather") == 0);
       std::vector<std::vector<int>> rest;
@@ -614,14 +606,11 @@ namespace rgc {
       RGC_CUDA(cudaMemcpyAsync(d_table, lp.table.data(), lp.table.size() * sizeof(float2),
                                cudaMemcpyHostToDevice, c.stream));
       SpectrumParams P {};
-      if (!from_dist) {
-        for (int d = 0; d < 3; ++d) {
-          P.u[d] = src.prtls->col[RGC_Q_U][d];
-          P.e[d] = src.prtls->col[RGC_Q_E][d];
-          P.b[d] = src.prtls->col[RGC_Q_B][d];
-        }
+      for (int d = 0; d < 3; ++d) {
+        P.u[d] = src.prtls->col[RGC_Q_U][d];
+        P.e[d] = src.prtls->col[RGC_Q_E][d];
+        P.b[d] = src.prtls->col[RGC_Q_B][d];
       }
-      P.cw_in     = src.cw_dev;
       P.nprtl     = src.n;
       P.a_fx      = d_afx;
       P.table     = d_table;
@@ -644,11 +633,7 @@ namespace rgc {
                                std::max<std::size_t>((std::size_t)(kTile + 2 * kWarps) * sizeof(int2),
                                                      (std::size_t)kWarps * lp.gpw * 32 * sizeof(double));
       RGC_CUDA(cudaEventRecord(c.ev[2], c.stream));
-      if (from_dist) {
-        launch_spectrum<true>(lp.gpw, dim3(nctas), smem, c.stream, P);
-      } else {
-        launch_spectrum<false>(lp.gpw, dim3(nctas), smem, c.stream, P);
-      }
+      launch_spectrum(lp.gpw, dim3(nctas), smem, c.stream, P);
       RGC_CUDA(cudaGetLastError());
       RGC_CUDA(cudaEventRecord(c.ev[3], c.stream));
       const int nslots = lp.ngroups * 32;
@@ -665,7 +650,7 @@ namespace rgc {
       RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]));
       main_ms += ms;
     }
-    if (!from_dist) {
+    {
       poison_all_kernel<<<(unsigned)((nbins + 127) / 128), 128, 0, c.stream>>>(d_poison, (int)nbins,
                                                                                d_acc);
       RGC_CUDA(cudaGetLastError());
@@ -728,7 +713,7 @@ extern "C" {
     src.g_syn = g_syn;
     src.e_at  = e_syn_at_g_syn;
     std::vector<double> acc;
-    RGC_TRY(run_spectrum(src, false, bins_e_syn, nbins, tab_x, tab_y, tab_n, true, acc));
+    RGC_TRY(run_spectrum(src, bins_e_syn, nbins, tab_x, tab_y, tab_n, true, acc));
     finish_spectrum(acc, bins_e_syn, nbins, out_spec, out_spec64);
     return RGC_OK;
   }
