@@ -1,6 +1,6 @@
 """Multi-GPU parity check (run under torchrun, one rank per GPU):
 
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/dist_check.py
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tests/tools/dist_check.py
 
 Every rank owns shard_range(n, rank, world) of one seeded host population; the NCCL
 all-reduced spectrum / histogram of the sharded run must match the CPU oracle on the
@@ -11,7 +11,7 @@ import os
 import sys
 from pathlib import Path
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import numpy as np
 import torch
 import torch.distributed as dist

@@ -2,7 +2,7 @@
 cases of tests/): random particle counts, bin counts and ranges, constants and
 populations (power laws, mono-energetic, zeros / NaNs / infs mixed in).
 
-    python tools/fuzz_parity.py [cases] [seed]
+    python tests/tools/fuzz_parity.py [cases] [seed]
 
 Bars: spectrum <= 1e-5 per bin on bins >= 1e-3 * max and <= 1e-4 on bins in
 [1e-6, 1e-3) * max (see two_tier_err); degenerate populations (fewer than 4095 particles,
@@ -14,7 +14,7 @@ every bin >= 1e-6 * max."""
 import sys
 from pathlib import Path
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import numpy as np
 
 import oracle
@@ -112,7 +112,7 @@ for case in range(ncases):
             ok = False
             j = int(np.argmax(np.where(big, np.abs(got - want) / np.abs(np.where(want == 0, 1, want)), 0)))
             why.append(f"rel err {err:.2e} at bin {j}: got {got[j]:.9e} want {want[j]:.9e} max {np.nanmax(np.abs(want[finite])):.3e}")
-            dump = Path(__file__).resolve().parents[1] / "gpurun_out"
+            dump = Path(__file__).resolve().parents[2] / "gpurun_out"
             dump.mkdir(exist_ok=True)
             np.savez_compressed(dump / f"fuzz_fail_s{seed}_c{case}.npz", U=np.array(U), E=np.array(E), B=np.array(B),
                                 bins=bins, consts=np.array(consts), got=got, want=want)

@@ -6,7 +6,7 @@ same formula evaluated in float64 on the same float table."""
 import sys
 from pathlib import Path
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import numpy as np
 
 import oracle

@@ -1,4 +1,4 @@
-"""Re-run a case dumped by tools/fuzz_parity.py (gpurun_out/fuzz_fail_*.npz)."""
+"""Re-run a case dumped by tests/tools/fuzz_parity.py (gpurun_out/fuzz_fail_*.npz)."""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
