@@ -226,6 +226,12 @@ int rgc_last_kernel_ms(float ms[2]);
  * (sync_prologue_kernel), [3] its bucket-sort kernels (column scan + sync_sort_kernel) */
 int rgc_last_kernel_times(float* ms, int n);
 
+/* Hinge evaluations (32 per lane group and sorted entry) the pair kernel actually issued
+ * in the last rgc_sync_spectrum_particles call on this rank: lane groups whose bins are
+ * all beyond the table's zero tail for a bucket are skipped, so this is <= the
+ * particles x bins of the call rounded up to whole groups (roofline accounting). */
+int rgc_last_pair_lane_evals(double* lane_evals);
+
 /* Roofline denominators measured on the device, on the compute stream (bench
  * harness only; MEASURED_PEAKS.json has no FP32 / shared-memory entry).
  * kind 0: FFMA GFLOP/s; 1: G evaluations/s of the pair loop's FADD.SAT+FFMA mix;

@@ -77,6 +77,7 @@ SIGNATURES = {
                                   _f32p, _f64p]),
     "rgc_last_kernel_ms": (C.c_int, [_f32p]),
     "rgc_last_kernel_times": (C.c_int, [_f32p, C.c_int]),
+    "rgc_last_pair_lane_evals": (C.c_int, [_f64p]),
     "rgc_measure_peak": (C.c_int, [C.c_int, _f64p, _f64p]),
     "rgc_h5_open": (C.c_int, [C.c_char_p, C.c_int, _vpp]),
     "rgc_h5_close": (C.c_int, [_vp]),
@@ -181,6 +182,13 @@ def last_kernel_times():
     ms = (C.c_float * 4)()
     check(lib().rgc_last_kernel_times(ms, 4))
     return tuple(float(x) for x in ms)
+
+
+def last_pair_lane_evals() -> float:
+    """hinge evaluations the pair kernel issued in the last particle-spectrum call"""
+    v = C.c_double()
+    check(lib().rgc_last_pair_lane_evals(C.byref(v)))
+    return float(v.value)
 
 
 PEAK_FFMA, PEAK_PAIR, PEAK_LDS64, PEAK_HBM_READ, PEAK_INT = range(5)

@@ -65,7 +65,8 @@ namespace rgc {
     cudaEvent_t stage_free[kNumStages] { nullptr, nullptr };
     // event pair for rgc_last_kernel_ms
     cudaEvent_t ev[6] { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-    float       last_ms[4] { 0.f, 0.f, 0.f, 0.f }; // total, dominant kernel, prologue kernel, -
+    float       last_ms[4] { 0.f, 0.f, 0.f, 0.f }; // total, dominant kernel, prologue kernel, sort
+    double      last_lane_evals { 0.0 }; // hinge evaluations the pair kernel issued in the last call
     // NCCL (dlopen'ed lazily)
     void* nccl_comm { nullptr };
     int   rank { 0 };

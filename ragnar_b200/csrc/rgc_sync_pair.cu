@@ -64,6 +64,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 namespace rgc {
@@ -113,6 +114,7 @@ namespace rgc {
     float2*     sorted; // (fc, w) in global bucket order, every bucket padded to an even length
     float2*     piece_mom; // [piece] {S0, S1} of the piece (float sums of <= kPieceLen terms)
     int*        poison;    // != 0: a particle's chiR overflows float (see pair_prologue)
+    unsigned long long* lane_evals; // hinge evaluations the pair kernel issued (roofline accounting)
     double*     partials;  // [cta][nslots] hinge sums
     int         nslots;
     // shared-memory layout of the pair kernel (byte offsets, computed once on the host)
@@ -764,6 +766,7 @@ namespace rgc {
     const int npieces = pstart[nb];
     const int wstride = (gridDim.x * kPWarps) / P.ncols;
     unsigned  tstage  = 0; // stages issued so far by this warp (ring slot and parity)
+    unsigned long long lane_evals = 0; // hinge evaluations issued by this warp (32 per group and entry)
 
     for (int piece = (blockIdx.x * kPWarps + warp) / P.ncols; piece < npieces; piece += wstride) {
       // bucket of the piece: first b with pstart[b + 1] > piece
@@ -781,6 +784,32 @@ namespace rgc {
       const int end  = min(beg + kPieceLen, bstart[b + 1]);
       const int nst  = (end - beg + kStageLen - 1) / kStageLen;
       const float2* src = P.sorted + beg;
+      // coefficients of this warp's lanes for the bucket, and the number NA of leading
+      // lane groups that can receive anything: a group whose 32 lanes all sit on zero cell
+      // pairs (x0 = e_syn / e_peak beyond the table's zero tail; bins ascend, so these are
+      // the trailing groups) has ds = 0 in every lane and is not evaluated at all — the
+      // reference's own `x0 >= xmax -> yfill` early-out, at group granularity.  Group 0
+      // carries the moment lanes of column 0 and always runs there.
+      float fap[GPW], sgn[GPW], ds[GPW], s2[GPW], s2p[GPW];
+      unsigned active = 0;
+#pragma unroll
+      for (int g = 0; g < GPW; ++g) {
+        const float4 dh = coef[max(aoff[g] + b, 0)];
+        ds[g]  = dh.x;
+        sgn[g] = dh.z;
+        fap[g] = (fa0[g] - dh.y) * dh.z;
+        s2[g]  = 0.0f;
+        s2p[g] = 0.0f;
+        active |= __any_sync(0xffffffffu, dh.x != 0.0f) ? (1u << g) : 0u;
+      }
+      if (col == 0) {
+        active |= 1u;
+      }
+      if (active == 0u) {
+        continue; // nothing of this column's bins is on the table for this bucket
+      }
+      const int na = 32 - __clz(active);
+      lane_evals += (unsigned long long)(end - beg) * (unsigned)(na * 32);
       auto issue = [&](int s) { // stage s of this piece -> ring slot (tstage + s) % kStages
         const unsigned slot  = (tstage + (unsigned)s) % kStages;
         const int      cnt   = min(kStageLen, end - beg - s * kStageLen);
@@ -798,86 +827,99 @@ namespace rgc {
       // chains bound the rounding drift of long runs of identical addends (a mono-energetic
       // population, where the drift is one-sided and the same in every piece) to ~1e-5;
       // folding every 64 entries would give 3e-6 for 5 % of this kernel's time
-      float fap[GPW], sgn[GPW], ds[GPW], s2[GPW], s2p[GPW];
-#pragma unroll
-      for (int g = 0; g < GPW; ++g) {
-        const float4 dh = coef[max(aoff[g] + b, 0)];
-        ds[g]  = dh.x;
-        sgn[g] = dh.z;
-        fap[g] = (fa0[g] - dh.y) * dh.z;
-        s2[g]  = 0.0f;
-        s2p[g] = 0.0f;
-      }
+      auto run_piece = [&](auto na_tag) {
+        constexpr int NA = decltype(na_tag)::value;
 #define RGC_PAIR_ONE(FC, W)                                                         \
   {                                                                                 \
-    float r[GPW];                                                                   \
-    _Pragma("unroll") for (int g = 0; g < GPW; ++g) { r[g] = __saturatef(fmaf((FC), sgn[g], fap[g])); } \
-    _Pragma("unroll") for (int g = 0; g < GPW; ++g) { s2[g] = fmaf((W), r[g], s2[g]); }    \
+    float r[NA];                                                                    \
+    _Pragma("unroll") for (int g = 0; g < NA; ++g) { r[g] = __saturatef(fmaf((FC), sgn[g], fap[g])); } \
+    _Pragma("unroll") for (int g = 0; g < NA; ++g) { s2[g] = fmaf((W), r[g], s2[g]); }     \
   }
 #define RGC_PAIR_BODY(Q) RGC_PAIR_ONE((Q).x, (Q).y) RGC_PAIR_ONE((Q).z, (Q).w)
-      for (int s = 0; s < nst; ++s) {
-        const unsigned t    = tstage + (unsigned)s;
-        const unsigned slot = t % kStages;
-        mbar_wait(&bars[slot], (t / kStages) & 1u);
-        const float4* buf = ring + slot * (kStageLen / 2);
-        const int     nq  = min(kStageLen, end - beg - s * kStageLen) >> 1; // float4 = 2 entries
-        if (nq == kStageLen / 2) {
-          // Two particles per broadcast LDS.128; the loads of the next two float4 are in
-          // flight while the current two are consumed (ping-pong registers).  Per particle
-          // all hinges first, then all accumulates, so no FFMA waits on the FFMA.SAT
-          // just before it.
-          float4 q0 = buf[0];
-          float4 q1 = buf[1];
+        for (int s = 0; s < nst; ++s) {
+          const unsigned t    = tstage + (unsigned)s;
+          const unsigned slot = t % kStages;
+          mbar_wait(&bars[slot], (t / kStages) & 1u);
+          const float4* buf = ring + slot * (kStageLen / 2);
+          const int     nq  = min(kStageLen, end - beg - s * kStageLen) >> 1; // float4 = 2 entries
+          if (nq == kStageLen / 2) {
+            // Two particles per broadcast LDS.128; the loads of the next two float4 are in
+            // flight while the current two are consumed (ping-pong registers).  Per particle
+            // all hinges first, then all accumulates, so no FFMA waits on the FFMA.SAT
+            // just before it.
+            float4 q0 = buf[0];
+            float4 q1 = buf[1];
 #pragma unroll 1
-          for (int p = 0; p < kStageLen / 2 - 4; p += 4) {
-            const float4 a0 = buf[p + 2];
-            const float4 a1 = buf[p + 3];
-            RGC_PAIR_BODY(q0)
-            RGC_PAIR_BODY(q1)
-            q0 = buf[p + 4];
-            q1 = buf[p + 5];
-            RGC_PAIR_BODY(a0)
-            RGC_PAIR_BODY(a1)
+            for (int p = 0; p < kStageLen / 2 - 4; p += 4) {
+              const float4 a0 = buf[p + 2];
+              const float4 a1 = buf[p + 3];
+              RGC_PAIR_BODY(q0)
+              RGC_PAIR_BODY(q1)
+              q0 = buf[p + 4];
+              q1 = buf[p + 5];
+              RGC_PAIR_BODY(a0)
+              RGC_PAIR_BODY(a1)
+            }
+            {
+              const float4 a0 = buf[kStageLen / 2 - 2];
+              const float4 a1 = buf[kStageLen / 2 - 1];
+              RGC_PAIR_BODY(q0)
+              RGC_PAIR_BODY(q1)
+              RGC_PAIR_BODY(a0)
+              RGC_PAIR_BODY(a1)
+            }
+          } else {
+            for (int p = 0; p < nq; ++p) {
+              const float4 q = buf[p];
+              RGC_PAIR_BODY(q)
+            }
           }
-          {
-            const float4 a0 = buf[kStageLen / 2 - 2];
-            const float4 a1 = buf[kStageLen / 2 - 1];
-            RGC_PAIR_BODY(q0)
-            RGC_PAIR_BODY(q1)
-            RGC_PAIR_BODY(a0)
-            RGC_PAIR_BODY(a1)
+          __syncwarp();
+          if (lane == 0 && s + kStages < nst) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(s + kStages);
           }
-        } else {
-          for (int p = 0; p < nq; ++p) {
-            const float4 q = buf[p];
-            RGC_PAIR_BODY(q)
-          }
-        }
-        __syncwarp();
-        if (lane == 0 && s + kStages < nst) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          issue(s + kStages);
-        }
-        if ((s & 3) == 3 || s + 1 == nst) { // every 256 entries
+          if ((s & 3) == 3 || s + 1 == nst) { // every 256 entries
 #pragma unroll
-          for (int g = 0; g < GPW; ++g) {
-            s2p[g] += s2[g];
-            s2[g] = 0.0f;
+            for (int g = 0; g < NA; ++g) {
+              s2p[g] += s2[g];
+              s2[g] = 0.0f;
+            }
           }
         }
-      }
 #undef RGC_PAIR_BODY
 #undef RGC_PAIR_ONE
+      };
+      switch (na) {
+#define RGC_NA_CASE(N)                                            \
+  case N:                                                         \
+    if constexpr (N <= GPW) {                                     \
+      run_piece(std::integral_constant<int, N> {});               \
+    }                                                             \
+    break;
+        RGC_NA_CASE(1)
+        RGC_NA_CASE(2)
+        RGC_NA_CASE(3)
+        RGC_NA_CASE(4)
+        RGC_NA_CASE(5)
+        RGC_NA_CASE(6)
+        RGC_NA_CASE(7)
+        RGC_NA_CASE(8)
+#undef RGC_NA_CASE
+      }
       tstage += (unsigned)nst;
 #pragma unroll
       for (int g = 0; g < GPW; ++g) {
         accd[g] = fma((double)ds[g], (double)s2p[g], accd[g]);
       }
-      if (col == 0 && lane >= 30) {
-        // spare lanes 30 / 31 of the last group carry S0 / S1 of this piece
+      if (col == 0 && lane < 2) {
+        // moment lanes 0 / 1 of group 0 carry S0 / S1 of this piece
         float* pm = reinterpret_cast<float*>(P.piece_mom + piece);
-        pm[lane - 30] = s2p[GPW - 1];
+        pm[lane] = s2p[0];
       }
+    }
+    if (lane == 0 && lane_evals != 0ull) {
+      atomicAdd(P.lane_evals, lane_evals);
     }
 
     // ---- CTA reduction over the warps of a column (fixed order), one partial row per CTA
@@ -1046,7 +1088,9 @@ namespace rgc {
                                     (float)(tp.tx[k + 1] - (double)k), 1.0f, 0.0f);
       }
     }
-    // slots: every warp column keeps its last two lanes for S0 / S1
+    // slots: every warp column keeps its first two lanes for the moments S0 / S1 (group 0
+    // always runs in column 0; trailing groups are skipped when all their lanes sit on
+    // zero cells)
     const int cap1 = kPMaxGPW * 32 - 2;
     pp.ncols       = 1;
     while (pp.ncols < 8 && (nbin + pp.ncols - 1) / pp.ncols > cap1) {
@@ -1062,7 +1106,7 @@ namespace rgc {
     const int cap = pp.gpw * 32 - 2;
     for (int s = 0; s < nbin; ++s) {
       const int    c    = s / cap, r = s % cap;
-      const int    slot = c * pp.gpw * 32 + r;
+      const int    slot = c * pp.gpw * 32 + 2 + r;
       const double rel  = a[s] - amin;
       double       A    = std::floor(rel);
       float        fa   = (float)(rel - A);
@@ -1075,9 +1119,9 @@ namespace rgc {
       pp.bin_of_slot[slot] = bins[s];
     }
     for (int c = 0; c < pp.ncols; ++c) {
-      const int last = (c + 1) * pp.gpw * 32;
-      pp.slot_f[last - 2] = make_float2(2.0f, 0.0f); // r = sat(1 + fc) = 1   -> S0
-      pp.slot_f[last - 1] = make_float2(1.0f, 0.0f); // r = sat(fc)     = fc  -> S1
+      const int first = c * pp.gpw * 32;
+      pp.slot_f[first]     = make_float2(2.0f, 0.0f); // r = sat(1 + fc) = 1   -> S0
+      pp.slot_f[first + 1] = make_float2(1.0f, 0.0f); // r = sat(fc)     = fc  -> S1
     }
   }
 
@@ -1279,6 +1323,7 @@ namespace rgc {
     P.counts    = reinterpret_cast<int*>(sb + off_cnt);
     P.tot       = reinterpret_cast<int*>(sb + off_tot);
     P.poison    = d_poison;
+    P.lane_evals = reinterpret_cast<unsigned long long*>(d_poison) + 1; // next 8 bytes of the result buffer
     P.sorted    = reinterpret_cast<float2*>(sb + off_sort);
     P.piece_mom = reinterpret_cast<float2*>(sb + off_mom);
     P.partials  = reinterpret_cast<double*>(sb + off_part);

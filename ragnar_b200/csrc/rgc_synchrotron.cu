@@ -659,10 +659,18 @@ namespace rgc {
     if (allreduce) {
       RGC_TRY(allreduce_sum_f64(d_acc, nbins));
     }
-    RGC_CUDA(cudaMemcpyAsync(acc_host.data(), d_acc, nbins * sizeof(double),
+    // one D2H: [per-bin sums | poison flag | issued hinge evaluations]
+    std::vector<double> back(nbins + 2);
+    RGC_CUDA(cudaMemcpyAsync(back.data(), d_acc, (nbins + 2) * sizeof(double),
                              cudaMemcpyDeviceToHost, c.stream));
     RGC_CUDA(cudaEventRecord(c.ev[1], c.stream));
     RGC_CUDA(cudaStreamSynchronize(c.stream));
+    std::copy(back.begin(), back.begin() + nbins, acc_host.begin());
+    {
+      unsigned long long le = 0;
+      std::memcpy(&le, &back[nbins + 1], sizeof(le));
+      c.last_lane_evals = (double)le;
+    }
     if (deferred && pair_single_pass(src.n)) {
       RGC_TRY(collect_pair_times(&main_ms));
     }
@@ -715,6 +723,13 @@ extern "C" {
     std::vector<double> acc;
     RGC_TRY(run_spectrum(src, bins_e_syn, nbins, tab_x, tab_y, tab_n, true, acc));
     finish_spectrum(acc, bins_e_syn, nbins, out_spec, out_spec64);
+    return RGC_OK;
+  }
+
+  int rgc_last_pair_lane_evals(double* lane_evals) {
+    if (lane_evals) {
+      *lane_evals = ctx().last_lane_evals;
+    }
     return RGC_OK;
   }
 

