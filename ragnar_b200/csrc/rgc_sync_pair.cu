@@ -1103,9 +1103,17 @@ namespace rgc {
     pp.slot_i.assign(pp.nslots, make_int2(-(1 << 20), 0));
     pp.slot_f.assign(pp.nslots, make_float2(1.0f, 0.0f));
     pp.bin_of_slot.assign(pp.nslots, -1);
-    const int cap = pp.gpw * 32 - 2;
+    // bins in ascending energy, dealt round-robin to the warp columns: every column then
+    // spans the whole energy range with ascending lanes (so the groups a bucket cannot
+    // reach are its TRAILING ones, in every column alike, and the columns' costs balance)
+    std::vector<int> order(nbin);
     for (int s = 0; s < nbin; ++s) {
-      const int    c    = s / cap, r = s % cap;
+      order[s] = s;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return a[x] < a[y]; });
+    for (int k = 0; k < nbin; ++k) {
+      const int    s    = order[k];
+      const int    c    = k % pp.ncols, r = k / pp.ncols;
       const int    slot = c * pp.gpw * 32 + 2 + r;
       const double rel  = a[s] - amin;
       double       A    = std::floor(rel);
