@@ -47,13 +47,13 @@ CONSTS = (1.0, 1.0, 1.0)  # B0, g_syn, e_syn_at_g_syn
 SEED = 123
 CPU_SAMPLE = 10_000_000  # particles per CPU-baseline step (x 200 bins = 2e9 evals, ~10 s on 16 cores)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload, from the
-# committed `ncu --set full` capture profiles/r1_ncu_full_v6_summary.json (not measurable
+# committed `ncu --set full` capture profiles/r1_ncu_full_v7_summary.json (not measurable
 # live: a number printed under a profiler is never a bench value)
 NCU_TRAFFIC_BYTES = {
-    "sync_pair_kernel": 0.800085e9 + 4.982e6,
-    "sync_prologue_kernel": 3.600621e9 + 947.26e6,
-    "sync_sort_kernel": 1.009818e9 + 764.20e6,
-    "energy_hist_kernel": 1.200043e9 + 3.73e6,
+    "sync_pair_kernel": 0.800168e9 + 5.542e6,
+    "sync_prologue_kernel": 3.600554e9 + 944.69e6,
+    "sync_sort_kernel": 1.010174e9 + 763.34e6,
+    "energy_hist_kernel": 1.200057e9 + 3.21e6,
 }
 
 
@@ -389,7 +389,7 @@ def run_ours(args) -> None:
         "kernel": "sync_pair_kernel", "bound": "fp32",
         "achieved": achieved_tflops, "peak": ffma_peak_tflops, "unit": "TFLOP/s",
         "frac": achieved_tflops / ffma_peak_tflops, "traffic": traffic("sync_pair_kernel"),
-        "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r1_ncu_full_v6_summary.json); "
+        "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r1_ncu_full_v7_summary.json); "
                         "algorithmic: 8 B per particle = 0.8e9",
         "peak_source": "FFMA issue rate measured on this device by rgc_measure_peak(0) in this "
                        "run (of measured); achieved = issued hinge evaluations x 4 flop (FFMA.SAT + FFMA) "
