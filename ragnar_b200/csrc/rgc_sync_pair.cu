@@ -210,7 +210,7 @@ namespace rgc {
     // gamma^2 from the float squares, like `1.0 + ux * ux + uy * uy + uz * uz` in the
     // reference (each square rounded to float, then promoted)
     const PairConsts& K = P.kc;
-    const double g2 = ((1.0 + round24(K, dux * dux)) + round24(K, duy * duy)) + round24(K, duz * duz);
+    const double g2 = ((1.0 + (double)(ux * ux)) + (double)(uy * uy)) + (double)(uz * uz);
     const double rg  = rsqrt_nr(g2);
     const double beta_x = dux * rg, beta_y = duy * rg, beta_z = duz * rg;
     const double bde = fma(beta_z, dez, fma(beta_y, dey, beta_x * dex));
