@@ -142,3 +142,28 @@ def test_tristan_file_layout(tmp_path):
         for n, c in zip(names[3:], cols2):
             assert np.array_equal(f.read(f"{n}_2"), c)
         assert f.info("x_2")["dims"] == [40] and not f.read("x_2").any()
+
+
+def test_pipeline_write_results_legacy_dataset_names(tmp_path):
+    """ragnar_b200/pipeline.py writes what the retired driver wrote
+    (legacy/simulation.cpp.bak:39,60-64,156-159); host-only, no GPU needed"""
+    from ragnar_b200 import cabi, pipeline
+
+    pb = np.geomspace(1e-3, 1e3, 20).astype(np.float32)
+    gb = np.geomspace(0.1, 200, 10).astype(np.float32)
+    rep = pipeline.PipelineReport()
+    for st in (3, 4):
+        for label, sp in (("e-", 1), ("e+", 2)):
+            rep.results.append(pipeline.SpeciesResult(st, label, sp, 100, (gb * st).astype(np.float32),
+                                                      (pb * sp).astype(np.float32), (pb * sp).astype(np.float64)))
+    out = str(tmp_path / "spec.h5")
+    pipeline.write_results(out, rep, pb, gb, multi_step=True)
+    with cabi.H5File(out, "r") as f:
+        names = set(f.list("/"))
+        assert names == {"sync_photon_energy_mec2"} | {f"{k}_{lab}_{st}" for k in ("gammaM1", "distribution", "sync_intensity")
+                                                        for lab in ("e-", "e+") for st in (3, 4)}
+        assert np.array_equal(f.read("sync_intensity_e+_4"), pb * 2)
+        assert np.array_equal(f.read("distribution_e-_3"), gb * 3)
+    pipeline.write_results(out, rep.__class__(results=rep.results[:2]), pb, gb, multi_step=False)
+    with cabi.H5File(out, "r") as f:
+        assert {"sync_intensity_e-", "gammaM1_e+", "distribution_e+"} <= set(f.list("/"))
