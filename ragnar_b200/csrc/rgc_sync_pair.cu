@@ -174,7 +174,6 @@ namespace rgc {
     const double s  = a * rc;
     const double s2 = s * s; // <= 0.0295
     double       t  = fma(s2, K.k11, K.k9); // next term s^13/13 <= 2.5e-11 in log2
-
     t               = fma(s2, t, K.k7);
     t               = fma(s2, t, K.k5);
     t               = fma(s2, t, K.k3);

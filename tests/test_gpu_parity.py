@@ -253,3 +253,23 @@ def test_spectrum_infinite_field_poisons_every_bin(cabi, port):
     got = cabi.sync_spectrum_particles(_particles(cabi, U, E, B), bins, 1.0, 1.0, 1.0)[1]
     _, want = port.sync_spectrum_particles(U, E, B, bins, 1.0, 1.0, 1.0)
     assert np.all(np.isfinite(want)) and synth.rel_err(got, want) < SPEC_RTOL
+
+
+def test_sort_rank_variants_agree(cabi, monkeypatch):
+    """RGC_SORT_RANK=ballot (order guaranteed by construction) against the default
+    shared-atomic ranking of the sort kernel: same buckets, same sums"""
+    U, E, B = synth.full3d(300_000, seed=12)
+    bins = cabi.logspace(0.01, 1e5, 200)
+    p = _particles(cabi, U, E, B)
+    a = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)[1]
+    monkeypatch.setenv("RGC_SORT_RANK", "ballot")
+    b = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)[1]
+    b2 = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)[1]
+    monkeypatch.delenv("RGC_SORT_RANK")
+    assert np.array_equal(b, b2)
+    big = a >= 1e-6 * a.max()
+    assert np.max(np.abs(a[big] - b[big]) / a[big]) < 1e-6
+    assert np.array_equal(a == 0, b == 0)
+    # the hardware replays same-address lanes of one shared-atomic instruction in ascending
+    # lane order, which is the order the ballot ranking builds: bit-identical results
+    assert np.array_equal(a, b)
