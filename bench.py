@@ -490,6 +490,11 @@ def run_ours(args) -> None:
         "roofline_histogram_kernel": roofline_hist,
         "cpu_baseline": cpu_baseline,
         "other_configs": other,
+        "notes": "evals = particles x photon bins, every pair the reference's functor is launched for "
+                 "(SURVEY.md 8d). Pairs beyond the F table's zero tail contribute exactly 0 in the "
+                 "reference too (its x0 >= xmax early-out); the pair kernel skips them per group of 32 "
+                 "bins, so it issues roofline.issued_over_total of the pairs and the result is "
+                 "bit-identical to evaluating all of them.",
     }
     emit(line)
     if dist is not None:
