@@ -115,6 +115,7 @@ namespace rgc {
     float2*     piece_mom; // [piece] {S0, S1} of the piece (float sums of <= kPieceLen terms)
     int*        poison;    // != 0: a particle's chiR overflows float (see pair_prologue)
     unsigned long long* lane_evals; // hinge evaluations the pair kernel issued (roofline accounting)
+    unsigned force_groups;          // lane groups evaluated even when all their lanes sit on zero cells
     double*     partials;  // [cta][nslots] hinge sums
     int         nslots;
     // shared-memory layout of the pair kernel (byte offsets, computed once on the host)
@@ -804,6 +805,7 @@ namespace rgc {
       if (col == 0) {
         active |= 1u;
       }
+      active |= P.force_groups; // test knob RGC_PAIR_NO_SKIP: evaluate every group
       if (active == 0u) {
         continue; // nothing of this column's bins is on the table for this bucket
       }
@@ -1330,6 +1332,10 @@ namespace rgc {
     P.counts    = reinterpret_cast<int*>(sb + off_cnt);
     P.tot       = reinterpret_cast<int*>(sb + off_tot);
     P.poison    = d_poison;
+    {
+      const char* ns  = std::getenv("RGC_PAIR_NO_SKIP"); // test knob
+      P.force_groups  = (ns && ns[0] == '1') ? ((1u << pp.gpw) - 1u) : 0u;
+    }
     P.lane_evals = reinterpret_cast<unsigned long long*>(d_poison) + 1; // next 8 bytes of the result buffer
     P.sorted    = reinterpret_cast<float2*>(sb + off_sort);
     P.piece_mom = reinterpret_cast<float2*>(sb + off_mom);

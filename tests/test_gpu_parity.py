@@ -273,3 +273,21 @@ def test_sort_rank_variants_agree(cabi, monkeypatch):
     # the hardware replays same-address lanes of one shared-atomic instruction in ascending
     # lane order, which is the order the ballot ranking builds: bit-identical results
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("nbins,lo,hi", [(200, 0.01, 1e5), (1000, 1e-3, 1e6)])
+def test_zero_group_skipping_is_exact(cabi, monkeypatch, nbins, lo, hi):
+    """lane groups whose bins all lie beyond the table's zero tail for a bucket are not
+    evaluated: bit-identical to evaluating every group, with fewer evaluations issued"""
+    U, E, B = synth.config3(400_000, seed=4)
+    bins = cabi.logspace(lo, hi, nbins)
+    p = _particles(cabi, U, E, B)
+    a = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)[1]
+    issued = cabi.last_pair_lane_evals()
+    monkeypatch.setenv("RGC_PAIR_NO_SKIP", "1")
+    b = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)[1]
+    issued_all = cabi.last_pair_lane_evals()
+    monkeypatch.delenv("RGC_PAIR_NO_SKIP")
+    assert np.array_equal(a, b)
+    assert 0 < issued < 0.85 * issued_all
+    assert issued_all >= 400_000 * nbins * 0.99  # every group of every (valid) particle
