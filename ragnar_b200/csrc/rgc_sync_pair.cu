@@ -84,13 +84,13 @@ namespace rgc {
   // fp64 constants of the prologue, read as constant-bank operands (an immediate double
   // whose low word is not zero costs two UMOVs per use otherwise)
   struct PairConsts {
-    double sqrt2, k15, k13, k11, k9, k7, k5, k3, two_over_ln2, split24, magic, flt_max, ep_lo, ep_hi,
-      q_lo;
+    double l3, lm4, lm2, inv_ln2, split24, magic, flt_max, ep_lo, ep_hi, q_lo;
   };
 
   struct PairParams {
-    PairConsts   kc;
-    const float* u[3];
+    PairConsts     kc;
+    const double2* log_tab; // [256] {log2(1 + j/256), 1 / (1 + j/256)}
+    const float*   u[3];
     const float* e[3];
     const float* b[3];
     std::size_t  nprtl;
@@ -157,30 +157,24 @@ namespace rgc {
     return fma(r * 0.5, e, r);
   }
 
-  // log2 of a positive normal double, |error| < 3e-11: exponent + atanh series of
-  // the mantissa folded into [sqrt(1/2), sqrt(2)); the quotient (m-1)/(m+1) comes
-  // from a MUFU.RCP64H seed refined by one Newton step
-  __device__ __forceinline__ double log2_pos(const PairConsts& K, double x) {
-    const int hi = __double2hiint(x);
-    int       ex = ((hi >> 20) & 0x7ff) - 1023;
-    double    m  = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
-    if (m > K.sqrt2) {
-      m *= 0.5;
-      ex += 1;
-    }
-    const double a = m - 1.0, b = m + 1.0;
-    double       rc;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(b));
-    rc              = fma(rc, fma(-b, rc, 1.0), rc);
-    const double s  = a * rc;
-    const double s2 = s * s; // <= 0.0295
-    double       t  = fma(s2, K.k11, K.k9); // next term s^13/13 <= 2.5e-11 in log2
-    t               = fma(s2, t, K.k7);
-    t               = fma(s2, t, K.k5);
-    t               = fma(s2, t, K.k3);
-    t               = t * s2;
-    const double sc = s * K.two_over_ln2; // 2 / ln 2
-    return (double)ex + fma(sc, t, sc);
+  // log2 of a positive normal double that carries float precision (e_peak after its
+  // rounding: 24 significant bits), |error| < 1e-12: exponent + table over the top 8
+  // fraction bits, log2(m) = T[j] + log2(1 + r) with m = mh (1 + r), mh = 1 + j/256,
+  // r = (m - mh) / mh in [0, 2^-8) and a cubic in r (r^5 / 5 < 2e-13).  tab[j] = {log2(mh),
+  // 1 / mh}, staged in shared memory.  8 fp64 operations against 16 for the atanh series.
+  __device__ __forceinline__ double log2_f24(const PairConsts& K, const double2* __restrict__ tab,
+                                             double x) {
+    const int     hi = __double2hiint(x);
+    const int     ex = ((hi >> 20) & 0x7ff) - 1023;
+    const int     j  = (hi >> 12) & 0xff; // top 8 fraction bits
+    const double  m  = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    const double  mh = __hiloint2double((hi & 0x000ff000) | 0x3ff00000, 0);
+    const double2 t  = tab[j];
+    const double  r  = (m - mh) * t.y;
+    double        p  = fma(r, K.lm4, K.l3); // 1/3 - r/4
+    p                = fma(r, p, K.lm2);     // -1/2 + r (...)
+    p                = fma(r, p, 1.0);
+    return (double)ex + fma(r * p, K.inv_ln2, t.x);
   }
 
   // x rounded to float precision (24 significant bits, nearest) without leaving the
@@ -195,15 +189,16 @@ namespace rgc {
   // chiR, e_peak — in fp64 like the reference's promoted arithmetic, then the table
   // coordinate of e_peak split into bucket and fraction.  The float roundings of the
   // reference's sequence are kept (squares of U, chiR, e_peak); sqrt, quotients and
-  // log10 go through rsqrt_nr / log2_pos (error < 3e-11, i.e. 2e-10 cell: far below a float ulp).
+  // log10 go through rsqrt_nr / log2_f24 (error < 1e-12: far below a float ulp).
   // Returns true with (bucket, fc, w), false for a particle the reference skips.  A
   // particle that poisons the reference's result raises *P.poison (rare path): chiR =
   // real_t(sqrt(q) / B0) = +inf makes e_peak = +inf > 0, x0 = e_syn / e_peak = 0 < xmin,
   // F = yfill = 0 and the term e_syn * inf * 0 = NaN in EVERY photon bin
   // (synchrotron.hpp:162-171).
-  __device__ __forceinline__ bool pair_prologue(const PairParams& P, float ux, float uy, float uz,
-                                               float ex, float ey, float ez, float bx, float by,
-                                               float bz, unsigned& bucket, float& fc, float& w) {
+  __device__ __forceinline__ bool pair_prologue(const PairParams& P, const double2* __restrict__ ltab,
+                                               float ux, float uy, float uz, float ex, float ey,
+                                               float ez, float bx, float by, float bz,
+                                               unsigned& bucket, float& fc, float& w) {
     const double dux = (double)ux, duy = (double)uy, duz = (double)uz;
     const double dex = (double)ex, dey = (double)ey, dez = (double)ez;
     const double dbx = (double)bx, dby = (double)by, dbz = (double)bz;
@@ -243,7 +238,7 @@ namespace rgc {
       return false;
     }
     const double ep = round24(K, ep_d);
-    const double c  = fma(-log2_pos(K, ep), P.cells_per_octave, P.c0);
+    const double c  = fma(-log2_f24(K, ltab, ep), P.cells_per_octave, P.c0);
     if (!(c >= P.c_lo && c < P.c_hi)) {
       return false;
     }
@@ -371,11 +366,13 @@ namespace rgc {
   template <int MINB>
   __global__ void __launch_bounds__(kPThreads, MINB)
     sync_prologue_kernel(const __grid_constant__ PairParams P) {
-    __shared__ int hist[kPMaxBuckets];
-    const int      tid = threadIdx.x;
+    __shared__ int     hist[kPMaxBuckets];
+    __shared__ double2 ltab[256];
+    const int          tid = threadIdx.x;
     for (int i = tid; i < P.nbp; i += kPThreads) {
       hist[i] = 0;
     }
+    ltab[tid] = P.log_tab[tid]; // kPThreads == 256
     __syncthreads();
     const int t0 = blockIdx.x * P.tiles_per_cta1;
     const int t1 = min(t0 + P.tiles_per_cta1, P.ntiles);
@@ -413,7 +410,7 @@ namespace rgc {
           float    fc = 0.0f, w = 0.0f;
           bool     ok = false;
           if (i0 + k < P.nprtl) {
-            ok = pair_prologue(P, f[0 * 4 + k], f[1 * 4 + k], f[2 * 4 + k], f[3 * 4 + k],
+            ok = pair_prologue(P, ltab, f[0 * 4 + k], f[1 * 4 + k], f[2 * 4 + k], f[3 * 4 + k],
                                f[4 * 4 + k], f[5 * 4 + k], f[6 * 4 + k], f[7 * 4 + k],
                                f[8 * 4 + k], bucket, fc, w);
           }
@@ -1149,7 +1146,27 @@ namespace rgc {
     return cache;
   }
 
+  static double2* g_log_tab = nullptr;
+
+  static int ensure_log_table(const double2** out) {
+    if (!g_log_tab) {
+      std::vector<double2> tab(256);
+      for (int j = 0; j < 256; ++j) {
+        const double mh = 1.0 + (double)j / 256.0;
+        tab[j]          = make_double2(std::log2(mh), 1.0 / mh);
+      }
+      RGC_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_log_tab), tab.size() * sizeof(double2)));
+      RGC_CUDA(cudaMemcpy(g_log_tab, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    }
+    *out = g_log_tab;
+    return RGC_OK;
+  }
+
   void pair_release_plans() {
+    if (g_log_tab) {
+      cudaFree(g_log_tab);
+      g_log_tab = nullptr;
+    }
     for (auto& e : plan_cache()) {
       if (e.dev) {
         cudaFree(e.dev);
@@ -1308,9 +1325,9 @@ namespace rgc {
     RGC_TRY(ensure_scratch(total, &scratch));
     char* sb = static_cast<char*>(scratch);
     PairParams P {};
-    P.kc = PairConsts { 1.4142135623730951, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0,
-                        1.0 / 5.0, 1.0 / 3.0, 2.8853900817779268, 536870913.0, 6755399441055744.0,
+    P.kc = PairConsts { 1.0 / 3.0, -0.25, -0.5, 1.4426950408889634, 536870913.0, 6755399441055744.0,
                         3.4028235677973366e38, 1e-37, 3.4028234e38, 1e-280 };
+    RGC_TRY(ensure_log_table(&P.log_tab));
     P.slot_i   = reinterpret_cast<const int2*>(cp->dev + cp->off_si);
     P.slot_f   = reinterpret_cast<const float2*>(cp->dev + cp->off_sf);
     P.coef_dh  = reinterpret_cast<const float4*>(cp->dev + cp->off_dh);
