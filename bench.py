@@ -76,7 +76,8 @@ def workload_config(n_per_gpu: int, nbins: int, ngpus: int, population: str = "c
         "photon_bin_range_mec2": list(PHOTON_BINS),
         "gamma_beta_bins": list(GAMMA_BINS),
         "population": "U1~u^-2 on [1,100], E=0, B isotropic unit (device Philox4x32-10, seed 123)",
-        "sharding": f"particles/{ngpus} ranks, NCCL all-reduce of spectra" if ngpus > 1 else "none",
+        "sharding": f"particles/{ngpus} ranks, all-reduce of the per-rank spectra and histograms "
+                    f"(peer-store exchange over NVLink, NCCL fallback)" if ngpus > 1 else "none",
         "cache": "inputs_larger_than_L2 (3.6 GB of particle columns per pass vs 126 MB L2)",
     }
 

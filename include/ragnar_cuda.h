@@ -82,6 +82,14 @@ int rgc_host_free(void* ptr);
 
 /* ------------------------------------------------- multi-GPU (one rank/GPU) */
 
+/* How result vectors are combined across ranks: 0 = single rank, 1 = ncclAllReduce,
+ * 2 = peer-store exchange — every rank's 1 MiB exchange buffer is mapped into every other
+ * rank (CUDA IPC, set up inside rgc_comm_init; handles travel through one ncclAllGather)
+ * and one kernel stores the rank's vector into all peers over NVLink, raises a flag and
+ * sums the slots in rank order.  Used for vectors of <= 8192 elements when all ranks share
+ * a node with peer access; RGC_XCHG=0 forces NCCL. */
+int rgc_comm_exchange_kind(int* kind);
+
 /* One process per GPU.  Rank 0 obtains an id, the launcher broadcasts its
  * RGC_COMM_ID_BYTES to all ranks out of band (torch.distributed / MPI / file),
  * every rank calls rgc_comm_init.  While a communicator is installed,

@@ -78,6 +78,7 @@ SIGNATURES = {
     "rgc_last_kernel_ms": (C.c_int, [_f32p]),
     "rgc_last_kernel_times": (C.c_int, [_f32p, C.c_int]),
     "rgc_last_pair_lane_evals": (C.c_int, [_f64p]),
+    "rgc_comm_exchange_kind": (C.c_int, [C.POINTER(C.c_int)]),
     "rgc_measure_peak": (C.c_int, [C.c_int, _f64p, _f64p]),
     "rgc_h5_open": (C.c_int, [C.c_char_p, C.c_int, _vpp]),
     "rgc_h5_close": (C.c_int, [_vp]),
@@ -182,6 +183,13 @@ def last_kernel_times():
     ms = (C.c_float * 4)()
     check(lib().rgc_last_kernel_times(ms, 4))
     return tuple(float(x) for x in ms)
+
+
+def comm_exchange_kind() -> str:
+    """how result vectors are combined across ranks"""
+    k = C.c_int()
+    check(lib().rgc_comm_exchange_kind(C.byref(k)))
+    return {0: "single rank", 1: "ncclAllReduce", 2: "peer-store exchange over NVLink"}[k.value]
 
 
 def last_pair_lane_evals() -> float:

@@ -71,6 +71,12 @@ namespace rgc {
     void* nccl_comm { nullptr };
     int   rank { 0 };
     int   nranks { 1 };
+    // peer-store exchange over NVLink (rgc_runtime.cu: xchg_*): every rank's buffer is
+    // mapped into every other rank through CUDA IPC; small result vectors are all-reduced
+    // by one kernel (stores into all peers, a flag, sum in rank order) instead of NCCL
+    bool               xchg_ready { false };
+    void*              xchg_peer[8] { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    unsigned long long xchg_seq { 0 };
     // reusable device scratch (grown on demand, freed in rgc_finalize)
     void*       scratch { nullptr };
     std::size_t scratch_bytes { 0 };

@@ -135,6 +135,9 @@ namespace rgc {
     ncclResult_t (*CommDestroy)(ncclComm_t) { nullptr };
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t,
                               ncclComm_t, cudaStream_t) { nullptr };
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) {
+      nullptr
+    };
     ncclResult_t (*GroupStart)() { nullptr };
     ncclResult_t (*GroupEnd)() { nullptr };
     const char* (*GetErrorString)(ncclResult_t) { nullptr };
@@ -170,6 +173,7 @@ namespace rgc {
     RGC_NCCL_SYM(CommInitRank, "ncclCommInitRank");
     RGC_NCCL_SYM(CommDestroy, "ncclCommDestroy");
     RGC_NCCL_SYM(AllReduce, "ncclAllReduce");
+    RGC_NCCL_SYM(AllGather, "ncclAllGather");
     RGC_NCCL_SYM(GroupStart, "ncclGroupStart");
     RGC_NCCL_SYM(GroupEnd, "ncclGroupEnd");
     RGC_NCCL_SYM(GetErrorString, "ncclGetErrorString");
@@ -186,10 +190,204 @@ namespace rgc {
     }                                                                               \
   } while (0)
 
+  // ------------------------------------------------- peer-store all-reduce (NVLink)
+  // Layout of every rank's exchange buffer: two sets (call parity) of
+  //   [kXchgMaxRanks][kXchgSlot] 8-byte elements   — slot r is written by rank r
+  //   [kXchgMaxRanks] flags, 128 B apart           — flag r = sequence number of rank r's data
+  // A call stores this rank's vector into slot `rank` of EVERY rank (its own included),
+  // fences, raises its flag everywhere, waits for all flags of its own buffer and sums
+  // the slots in rank order: the same order on every rank, so all ranks get bit-identical
+  // sums.  The other parity's set is only rewritten two calls later, when every peer has
+  // provably finished reading it (a rank raises flag k+1 after its call-k sum, in stream
+  // order).  One CTA; payloads <= kXchgSlot elements (larger ones go through NCCL).
+  constexpr int         kXchgMaxRanks = 8;
+  constexpr std::size_t kXchgSlot     = 8192; // elements
+  constexpr std::size_t kXchgSetBytes = kXchgMaxRanks * kXchgSlot * 8 + kXchgMaxRanks * 128;
+  constexpr std::size_t kXchgBytes    = 2 * kXchgSetBytes;
+
+  struct XchgParams {
+    unsigned long long* peer[kXchgMaxRanks];
+    int                 rank, nranks;
+    unsigned long long  seq;
+    unsigned long long* data; // in / out, n elements
+    int                 n;
+    int                 is_f64;
+  };
+
+  __global__ void __launch_bounds__(256) xchg_allreduce_kernel(const XchgParams P) {
+    const std::size_t set_off  = (P.seq & 1ull) * (kXchgSetBytes / 8);
+    const std::size_t flag_off = set_off + (std::size_t)kXchgMaxRanks * kXchgSlot;
+    // 1. my vector into slot `rank` of every rank
+    for (int p = 0; p < P.nranks; ++p) {
+      unsigned long long* dst = P.peer[p] + set_off + (std::size_t)P.rank * kXchgSlot;
+      for (int i = threadIdx.x; i < P.n; i += blockDim.x) {
+        dst[i] = P.data[i];
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. raise my flag everywhere, wait for everyone's flag here
+    if (threadIdx.x < P.nranks) {
+      unsigned long long* f = P.peer[threadIdx.x] + flag_off + (std::size_t)P.rank * 16;
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(P.seq) : "memory");
+      const unsigned long long* mine = P.peer[P.rank] + flag_off + (std::size_t)threadIdx.x * 16;
+      unsigned long long        v    = 0;
+      for (long long spin = 0; spin < (1ll << 24); ++spin) { // bounded: a dead peer must not hang the GPU
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        if (v >= P.seq) {
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    // 3. sum the slots in rank order
+    const unsigned long long* src = P.peer[P.rank] + set_off;
+    for (int i = threadIdx.x; i < P.n; i += blockDim.x) {
+      if (P.is_f64) {
+        double s = 0.0;
+        for (int r = 0; r < P.nranks; ++r) {
+          s += __longlong_as_double((long long)src[(std::size_t)r * kXchgSlot + i]);
+        }
+        P.data[i] = (unsigned long long)__double_as_longlong(s);
+      } else {
+        unsigned long long s = 0;
+        for (int r = 0; r < P.nranks; ++r) {
+          s += src[(std::size_t)r * kXchgSlot + i];
+        }
+        P.data[i] = s;
+      }
+    }
+  }
+
+  static int xchg_allreduce(void* dev, std::size_t n, bool is_f64) {
+    auto&      c = ctx();
+    XchgParams P {};
+    for (int r = 0; r < c.nranks; ++r) {
+      P.peer[r] = static_cast<unsigned long long*>(c.xchg_peer[r]);
+    }
+    P.rank   = c.rank;
+    P.nranks = c.nranks;
+    P.seq    = ++c.xchg_seq;
+    P.data   = static_cast<unsigned long long*>(dev);
+    P.n      = (int)n;
+    P.is_f64 = is_f64 ? 1 : 0;
+    xchg_allreduce_kernel<<<1, 256, 0, c.stream>>>(P);
+    RGC_CUDA(cudaGetLastError());
+    count_launch(1);
+    return RGC_OK;
+  }
+
+  // maps every rank's exchange buffer into this process (CUDA IPC; handles travel through
+  // one ncclAllGather).  Any failure leaves xchg_ready false: NCCL carries the exchange.
+  static int xchg_setup() {
+    auto& c = ctx();
+    c.xchg_ready = false;
+    const char* env = std::getenv("RGC_XCHG"); // "0": always NCCL
+    if ((env && env[0] == '0') || c.nranks < 2 || c.nranks > kXchgMaxRanks) {
+      return RGC_OK;
+    }
+    void* local = nullptr;
+    if (cudaMalloc(&local, kXchgBytes) != cudaSuccess) {
+      cudaGetLastError();
+      return RGC_OK;
+    }
+    cudaMemset(local, 0, kXchgBytes);
+    cudaDeviceSynchronize();
+    cudaIpcMemHandle_t mine;
+    bool               ok = cudaIpcGetMemHandle(&mine, local) == cudaSuccess;
+    // all-gather the handles (and whether every rank got this far)
+    unsigned char* dbuf = nullptr;
+    const std::size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    if (cudaMalloc(reinterpret_cast<void**>(&dbuf), rec * c.nranks) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(local);
+      return RGC_OK;
+    }
+    std::vector<unsigned char> hbuf(rec * c.nranks, 0);
+    std::memcpy(hbuf.data() + rec * c.rank, &mine, sizeof(mine));
+    hbuf[rec * c.rank + sizeof(mine)] = ok ? 1 : 0;
+    RGC_CUDA(cudaMemcpy(dbuf + rec * c.rank, hbuf.data() + rec * c.rank, rec, cudaMemcpyHostToDevice));
+    RGC_NCCL(nccl().AllGather(dbuf + rec * c.rank, dbuf, rec, ncclChar,
+                              static_cast<ncclComm_t>(c.nccl_comm), c.stream));
+    RGC_CUDA(cudaStreamSynchronize(c.stream));
+    RGC_CUDA(cudaMemcpy(hbuf.data(), dbuf, rec * c.nranks, cudaMemcpyDeviceToHost));
+    cudaFree(dbuf);
+    for (int r = 0; r < c.nranks; ++r) {
+      ok = ok && hbuf[rec * r + sizeof(mine)] == 1;
+    }
+    int opened = 0;
+    if (ok) {
+      for (int r = 0; r < c.nranks && ok; ++r) {
+        if (r == c.rank) {
+          c.xchg_peer[r] = local;
+          continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, hbuf.data() + rec * r, sizeof(h));
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          ok = false;
+          break;
+        }
+        c.xchg_peer[r] = ptr;
+        ++opened;
+      }
+    }
+    // every rank must agree before anyone stores into a peer: all-reduce the verdict
+    // (this is also the barrier behind the memsets above)
+    int* dflag = nullptr;
+    RGC_CUDA(cudaMalloc(reinterpret_cast<void**>(&dflag), sizeof(int)));
+    const int mine_ok = ok ? 0 : 1;
+    RGC_CUDA(cudaMemcpy(dflag, &mine_ok, sizeof(int), cudaMemcpyHostToDevice));
+    RGC_NCCL(nccl().AllReduce(dflag, dflag, 1, ncclInt32, ncclSum, static_cast<ncclComm_t>(c.nccl_comm),
+                              c.stream));
+    RGC_CUDA(cudaStreamSynchronize(c.stream));
+    int failed = 1;
+    RGC_CUDA(cudaMemcpy(&failed, dflag, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(dflag);
+    if (failed != 0) {
+      for (int r = 0; r < c.nranks; ++r) {
+        if (r != c.rank && c.xchg_peer[r]) {
+          cudaIpcCloseMemHandle(c.xchg_peer[r]);
+        }
+        c.xchg_peer[r] = nullptr;
+      }
+      cudaFree(local);
+      return RGC_OK;
+    }
+    c.xchg_seq   = 0;
+    c.xchg_ready = true;
+    (void)opened;
+    return RGC_OK;
+  }
+
+  static void xchg_teardown() {
+    auto& c = ctx();
+    if (!c.xchg_ready) {
+      return;
+    }
+    cudaStreamSynchronize(c.stream);
+    for (int r = 0; r < c.nranks; ++r) {
+      if (c.xchg_peer[r]) {
+        if (r == c.rank) {
+          cudaFree(c.xchg_peer[r]);
+        } else {
+          cudaIpcCloseMemHandle(c.xchg_peer[r]);
+        }
+        c.xchg_peer[r] = nullptr;
+      }
+    }
+    c.xchg_ready = false;
+  }
+
   int allreduce_sum_f64(double* dev, std::size_t n) {
     auto& c = ctx();
     if (!c.nccl_comm || c.nranks <= 1 || n == 0) {
       return RGC_OK;
+    }
+    if (c.xchg_ready && n <= kXchgSlot) {
+      return xchg_allreduce(dev, n, true);
     }
     RGC_NCCL(nccl().AllReduce(dev, dev, n, ncclFloat64, ncclSum,
                               static_cast<ncclComm_t>(c.nccl_comm), c.stream));
@@ -200,6 +398,9 @@ namespace rgc {
     auto& c = ctx();
     if (!c.nccl_comm || c.nranks <= 1 || n == 0) {
       return RGC_OK;
+    }
+    if (c.xchg_ready && n <= kXchgSlot) {
+      return xchg_allreduce(dev, n, false);
     }
     RGC_NCCL(nccl().AllReduce(dev, dev, n, ncclUint64, ncclSum,
                               static_cast<ncclComm_t>(c.nccl_comm), c.stream));
@@ -429,17 +630,27 @@ extern "C" {
     c.nccl_comm = comm;
     c.rank      = rank;
     c.nranks    = nranks;
+    RGC_TRY(xchg_setup());
     return RGC_OK;
   }
 
   int rgc_comm_destroy(void) {
     auto& c = ctx();
+    xchg_teardown();
     if (c.nccl_comm) {
       nccl().CommDestroy(static_cast<ncclComm_t>(c.nccl_comm));
       c.nccl_comm = nullptr;
     }
     c.rank   = 0;
     c.nranks = 1;
+    return RGC_OK;
+  }
+
+  int rgc_comm_exchange_kind(int* kind) {
+    if (kind) {
+      auto& c = ctx();
+      *kind   = (c.nccl_comm && c.nranks > 1) ? (c.xchg_ready ? 2 : 1) : 0;
+    }
     return RGC_OK;
   }
 

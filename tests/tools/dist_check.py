@@ -62,6 +62,7 @@ if rank == 0:
     ok = (err < 1e-5 and herr < 1e-5 and np.array_equal(counts, want_c)
           and np.array_equal(counts, solo_hist[1]) and add < 1e-6
           and np.array_equal(spec == 0, want == 0) and np.all(np.isfinite(spec0)))
+    print(f"[dist_check] world={world} exchange: {cabi.comm_exchange_kind()}", flush=True)
     print(f"[dist_check] world={world} n={n}: spectrum rel err vs oracle {err:.2e}, "
           f"weighted hist {herr:.2e}, counts bit-exact={np.array_equal(counts, want_c)}, "
           f"sharded vs one-rank spectrum {add:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
