@@ -2,10 +2,12 @@
 bootstrap of libragnar_cuda's own NCCL communicator.
 
 The data path has exactly one exchange step: every rank reduces its shard to
-`nbins` fp64 (+ u64 counts) and ONE ncclAllReduce(sum) per result vector combines
+`nbins` fp64 (+ u64 counts) and one all-reduce (sum) per result vector combines
 them, issued by the library on its compute stream right behind the reduction
-kernel (rgc_runtime.cu: allreduce_sum_*).  torch.distributed is used only to get
-the 128-byte NCCL unique id from rank 0 to the other ranks.  The reference has no
+kernel (rgc_runtime.cu: allreduce_sum_* — a peer-store kernel over NVLink when the
+ranks can map each other's exchange buffers, ncclAllReduce otherwise).
+torch.distributed is used only to get the 128-byte NCCL unique id from rank 0 to
+the other ranks.  The reference has no
 multi-GPU path at all.
 """
 from __future__ import annotations
