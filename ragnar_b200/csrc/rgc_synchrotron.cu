@@ -306,49 +306,16 @@ namespace rgc {
     }
   }
 
-  // ---- SynchrotronSpectrumFromDist (reference synchrotron.hpp:72-95): G x M pairs, at
-  // most a few million — latency-bound, so it is evaluated in fp64 with full-precision
-  // table coordinates (the fixed-point gather kernel resolves 1e-6 cell, which shows at
-  // the 1e-5 level next to the zeros of F when only a few hundred terms are summed).
-  // One thread per photon bin, the distribution staged in shared memory in chunks,
-  // terms added in distribution order: deterministic.
-  //   t = a_j + c_g,  F = v_k + s_k (t - k) in cell k = floor(t), 0 outside [0, T-1)
-  __global__ void __launch_bounds__(128)
-    sync_dist_kernel(const double* __restrict__ a, int nbins, const double2* __restrict__ cw, int ndist,
-                     const double2* __restrict__ coef_vs, int T, double* __restrict__ out) {
-    __shared__ double2 scw[256];
-    const int j  = blockIdx.x * blockDim.x + threadIdx.x;
-    const double aj = j < nbins ? a[j] : 0.0;
-    double acc = 0.0;
-    for (int g0 = 0; g0 < ndist; g0 += 256) {
-      const int cnt = min(256, ndist - g0);
-      __syncthreads();
-      for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-        scw[i] = cw[g0 + i];
-      }
-      __syncthreads();
-      if (j < nbins) {
-        for (int i = 0; i < cnt; ++i) {
-          const double t = aj + scw[i].x;
-          if (t >= 0.0 && t < (double)(T - 1)) { // x0 in [xmin, xmax); NaN coordinates fail
-            const double  k  = floor(t);
-            const double2 vs = coef_vs[(int)k];
-            acc = fma(scw[i].y, fma(vs.y, t - k, vs.x), acc);
-          }
-        }
-      }
-    }
-    if (j < nbins) {
-      out[j] = acc;
-    }
-  }
-
-  // a poisoned population: every bin becomes NaN, as in the reference
-  __global__ void poison_all_kernel(const int* __restrict__ poison, int nbins,
-                                    double* __restrict__ d_acc) {
+  // d_acc[j] = e_syn[j] * sum_i w_i F_ij — the factor every term of a bin shares, applied
+  // before the all-reduce so that every rank contributes finished values whichever path
+  // it took (the literal path's terms already carry it).  A poisoned population turns
+  // every bin into NaN, as in the reference.
+  __global__ void finalize_acc_kernel(const int* __restrict__ poison, int nbins,
+                                      const float* __restrict__ e_syn, double* __restrict__ d_acc) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < nbins && *poison != 0) {
-      d_acc[j] = __longlong_as_double(0x7ff8000000000000ll);
+    if (j < nbins) {
+      d_acc[j] = *poison != 0 ? __longlong_as_double(0x7ff8000000000000ll)
+                              : (double)e_syn[j] * d_acc[j];
     }
   }
 
@@ -536,22 +503,38 @@ namespace rgc {
     chunk_bins(tp, bins_e_syn, nbins, chunks, nan_bins);
 
     acc_host.assign(nbins, 0.0);
+    if (nbins == 0) {
+      return RGC_OK; // an empty Bins gives an empty Array1D (every rank alike)
+    }
     // per-bin sums are accumulated on the device (one small buffer that survives the
-    // scratch re-layouts of the launches), all-reduced once and read back once
+    // scratch re-layouts of the launches), all-reduced once and read back once:
+    // [nbins doubles | poison flag, issued evaluations | nbins floats: e_syn]
     void* result = nullptr;
-    RGC_TRY(ensure_result(nbins * sizeof(double) + 16, &result));
+    RGC_TRY(ensure_result(nbins * sizeof(double) + 16 + nbins * sizeof(float), &result));
     double* d_acc    = static_cast<double*>(result);
     int*    d_poison = reinterpret_cast<int*>(d_acc + nbins);
+    float*  d_bins   = reinterpret_cast<float*>(d_acc + nbins + 2);
     RGC_CUDA(cudaEventRecord(c.ev[0], c.stream));
     RGC_CUDA(cudaMemsetAsync(d_acc, 0, nbins * sizeof(double) + 16, c.stream));
     float main_ms  = 0.f;
     bool  deferred = false;
+    // ---- small populations: the reference's own float arithmetic per pair
+    // (rgc_sync_literal.cu); nothing averages its rounding there
+    const bool literal = src.n > 0 && src.n <= literal_max_n();
+    if (literal) {
+      RGC_TRY(run_spectrum_literal(src.prtls, src.n, src.B0, src.g_syn, src.e_at, nullptr, nullptr,
+                                   nullptr, bins_e_syn, nbins, tab_x, tab_y, tab_n, d_acc));
+      chunks.clear();
+      nan_bins.clear();
+    } else {
+      RGC_TRY(copy_h2d(d_bins, bins_e_syn, nbins * sizeof(float), c.stream));
+    }
     // ---- bucketed hinge path (rgc_sync_pair.cu) for every chunk it can take;
     // RGC_SPECTRUM_PATH=gather forces the gather kernel below (A/B checks)
     if (src.n == 0) {
       chunks.clear(); // a rank without particles launches nothing but still joins the all-reduce
     }
-    if (src.n > 0) {
+    if (src.n > 0 && !literal) {
       const char* force = std::getenv("RGC_SPECTRUM_PATH");
       const bool  allow = !(force && std::strcmp(force, "gather") == 0);
       std::vector<std::vector<int>> rest;
@@ -650,9 +633,9 @@ namespace rgc {
       RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]));
       main_ms += ms;
     }
-    {
-      poison_all_kernel<<<(unsigned)((nbins + 127) / 128), 128, 0, c.stream>>>(d_poison, (int)nbins,
-                                                                               d_acc);
+    if (!literal && src.n > 0) {
+      finalize_acc_kernel<<<(unsigned)((nbins + 127) / 128), 128, 0, c.stream>>>(d_poison, (int)nbins,
+                                                                                 d_bins, d_acc);
       RGC_CUDA(cudaGetLastError());
       count_launch(1);
     }
@@ -674,6 +657,10 @@ namespace rgc {
     if (deferred && pair_single_pass(src.n)) {
       RGC_TRY(collect_pair_times(&main_ms));
     }
+    if (literal) {
+      RGC_CUDA(cudaEventElapsedTime(&main_ms, c.ev[2], c.ev[3]));
+      c.last_ms[2] = c.last_ms[3] = 0.f;
+    }
     float total_ms = 0.f;
     RGC_CUDA(cudaEventElapsedTime(&total_ms, c.ev[0], c.ev[1]));
     c.last_ms[0] = total_ms;
@@ -684,15 +671,15 @@ namespace rgc {
     return RGC_OK;
   }
 
-  static void finish_spectrum(const std::vector<double>& acc, const float* bins_e_syn,
-                              std::size_t nbins, float* out_spec, double* out_spec64) {
+  // acc holds finished per-bin values (e_syn factor applied on the device)
+  static void finish_spectrum(const std::vector<double>& acc, std::size_t nbins, float* out_spec,
+                              double* out_spec64) {
     for (std::size_t j = 0; j < nbins; ++j) {
-      const double v = (double)bins_e_syn[j] * acc[j];
       if (out_spec64) {
-        out_spec64[j] = v;
+        out_spec64[j] = acc[j];
       }
       if (out_spec) {
-        out_spec[j] = (float)v;
+        out_spec[j] = (float)acc[j];
       }
     }
   }
@@ -722,7 +709,7 @@ extern "C" {
     src.e_at  = e_syn_at_g_syn;
     std::vector<double> acc;
     RGC_TRY(run_spectrum(src, bins_e_syn, nbins, tab_x, tab_y, tab_n, true, acc));
-    finish_spectrum(acc, bins_e_syn, nbins, out_spec, out_spec64);
+    finish_spectrum(acc, nbins, out_spec, out_spec64);
     return RGC_OK;
   }
 
@@ -745,67 +732,38 @@ extern "C" {
       return fail(RGC_ERR_INVALID, "SynchrotronSpectrumFromDist: grid too large");
     }
     auto& c = ctx();
-    TablePlan tp;
-    RGC_TRY(make_table_plan(tab_x, tab_y, tab_n, tp));
-    const int T = (int)tp.T;
-    // per cell k: value of the cell's line at t = k and its slope (the reference's
-    // interpolant between the ACTUAL nodes tx[k], tx[k+1]: tabulation.hpp:39-41)
-    std::vector<double2> vs(T);
-    for (int k = 0; k + 1 < T; ++k) {
-      const double sk = (tp.y[k + 1] - tp.y[k]) / (tp.tx[k + 1] - tp.tx[k]);
-      vs[k]           = make_double2(tp.y[k] + sk * ((double)k - tp.tx[k]), sk);
+    if (tab_n < 2) {
+      return fail(RGC_ERR_INVALID, "F table needs at least 2 points");
     }
-    vs[T - 1] = make_double2(0.0, 0.0);
-    // per distribution bin, on the host (ndist values): e_peak and the weight exactly as
-    // the reference forms them in float (synchrotron.hpp:78-79,90,92)
-    std::vector<double2> cw(ndist);
+    // per distribution bin, on the host (ndist values): e_peak exactly as the reference
+    // forms it in float (synchrotron.hpp:78-79); the term ((f * e_syn) [* gbeta]) * F is
+    // formed per pair by the literal kernel (synchrotron.hpp:89-93)
+    std::vector<float> ep(ndist);
     for (std::size_t g = 0; g < ndist; ++g) {
-      const float gb     = gbeta[g];
-      const float e_peak = e_syn_at_g_syn * gb * gb / (g_syn * g_syn);
-      const float weight = islog_bins_prtls ? f[g] * gb : f[g];
-      cw[g]              = make_double2(std::nan(""), 0.0); // NaN coordinate: contributes nothing
-      if (e_peak > 0.0f && std::isfinite(e_peak)) {
-        cw[g] = make_double2(-std::log10((double)e_peak) / tp.dL, (double)weight);
-      }
+      const float gb = gbeta[g];
+      ep[g]          = e_syn_at_g_syn * gb * gb / (g_syn * g_syn);
     }
-    std::vector<double> a(nbins);
-    for (std::size_t j = 0; j < nbins; ++j) {
-      const float e = bins_e_syn[j];
-      a[j] = (e > 0.0f && std::isfinite(e)) ? (std::log10((double)e) - tp.L0) / tp.dL : std::nan("");
-    }
-    auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
-    const std::size_t o_a   = 0;
-    const std::size_t o_cw  = align(o_a + nbins * sizeof(double));
-    const std::size_t o_vs  = align(o_cw + ndist * sizeof(double2));
-    const std::size_t o_out = align(o_vs + (std::size_t)T * sizeof(double2));
-    void*             scratch = nullptr;
-    RGC_TRY(ensure_scratch(o_out + nbins * sizeof(double), &scratch));
-    char* sb = static_cast<char*>(scratch);
+    void* result = nullptr;
+    RGC_TRY(ensure_result(nbins * sizeof(double), &result));
+    double* d_out = static_cast<double*>(result);
     RGC_CUDA(cudaEventRecord(c.ev[0], c.stream));
-    RGC_TRY(copy_h2d(sb + o_a, a.data(), nbins * sizeof(double), c.stream));
-    RGC_TRY(copy_h2d(sb + o_cw, cw.data(), ndist * sizeof(double2), c.stream));
-    RGC_TRY(copy_h2d(sb + o_vs, vs.data(), (std::size_t)T * sizeof(double2), c.stream));
-    RGC_CUDA(cudaEventRecord(c.ev[2], c.stream));
-    sync_dist_kernel<<<(unsigned)((nbins + 127) / 128), 128, 0, c.stream>>>(
-      reinterpret_cast<const double*>(sb + o_a), (int)nbins,
-      reinterpret_cast<const double2*>(sb + o_cw), (int)ndist,
-      reinterpret_cast<const double2*>(sb + o_vs), T, reinterpret_cast<double*>(sb + o_out));
-    RGC_CUDA(cudaGetLastError());
-    count_launch(1);
-    RGC_CUDA(cudaEventRecord(c.ev[3], c.stream));
+    if (ndist == 0) {
+      RGC_CUDA(cudaMemsetAsync(d_out, 0, nbins * sizeof(double), c.stream));
+      RGC_CUDA(cudaEventRecord(c.ev[2], c.stream));
+      RGC_CUDA(cudaEventRecord(c.ev[3], c.stream));
+    } else {
+      RGC_TRY(run_spectrum_literal(nullptr, ndist, 1.0f, g_syn, e_syn_at_g_syn, ep.data(), f,
+                                   islog_bins_prtls ? gbeta : nullptr, bins_e_syn, nbins, tab_x,
+                                   tab_y, tab_n, d_out));
+    }
     std::vector<double> acc(nbins);
-    RGC_CUDA(cudaMemcpyAsync(acc.data(), sb + o_out, nbins * sizeof(double), cudaMemcpyDeviceToHost,
+    RGC_CUDA(cudaMemcpyAsync(acc.data(), d_out, nbins * sizeof(double), cudaMemcpyDeviceToHost,
                              c.stream));
     RGC_CUDA(cudaEventRecord(c.ev[1], c.stream));
     RGC_CUDA(cudaStreamSynchronize(c.stream));
     RGC_CUDA(cudaEventElapsedTime(&c.last_ms[0], c.ev[0], c.ev[1]));
     RGC_CUDA(cudaEventElapsedTime(&c.last_ms[1], c.ev[2], c.ev[3]));
-    for (std::size_t j = 0; j < nbins; ++j) {
-      if (std::isnan(bins_e_syn[j])) {
-        acc[j] = std::nan(""); // as in the particle path; e <= 0 gives 0, +inf gives inf * 0
-      }
-    }
-    finish_spectrum(acc, bins_e_syn, nbins, out_spec, out_spec64);
+    finish_spectrum(acc, nbins, out_spec, out_spec64);
     return RGC_OK;
   }
 

@@ -56,5 +56,7 @@ def rel_err(got, want, floor_frac=1e-6):
     """max relative error over bins whose reference value is >= floor_frac * max"""
     got = np.asarray(got, np.float64)
     want = np.asarray(want, np.float64)
-    keep = want >= floor_frac * want.max()
+    keep = (want >= floor_frac * want.max()) & (want > 0)
+    if not keep.any():
+        return 0.0
     return float(np.max(np.abs(got[keep] - want[keep]) / want[keep]))
