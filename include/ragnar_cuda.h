@@ -87,7 +87,10 @@ int rgc_host_free(void* ptr);
  * rank (CUDA IPC, set up inside rgc_comm_init; handles travel through one ncclAllGather)
  * and one kernel stores the rank's vector into all peers over NVLink, raises a flag and
  * sums the slots in rank order.  Used for vectors of <= 8192 elements when all ranks share
- * a node with peer access; RGC_XCHG=0 forces NCCL. */
+ * a node with peer access; RGC_XCHG=0 forces NCCL.  The wait for the peers' flags is bounded in
+ * time (RGC_XCHG_TIMEOUT_MS, default 600000): when a peer never delivers, the call that issued
+ * the exchange returns RGC_ERR_NCCL (its result is poisoned, never a partial sum) and the
+ * exchange stays unusable until the communicator is destroyed and re-created. */
 int rgc_comm_exchange_kind(int* kind);
 
 /* One process per GPU.  Rank 0 obtains an id, the launcher broadcasts its
@@ -199,7 +202,10 @@ int rgc_energy_histogram(const rgc_particles_t* p, size_t nactive, const float* 
  * checked by the caller, synchrotron.hpp:139-142); (tab_x, tab_y): the F(x) table
  * of sync::TabulateFfunc (log grid).  out_spec[nbins] float, out_spec64 (optional)
  * the fp64 sums it was rounded from.  All-reduced over ranks when a communicator
- * is installed. */
+ * is installed; every rank must make the call (p may be NULL / unallocated with
+ * nactive = 0: an empty shard that still joins the all-reduce).  Populations of up to
+ * RGC_LITERAL_MAX_N particles (default 2^19) are evaluated with the reference's own
+ * float arithmetic per pair (rgc_sync_literal.cu), larger ones by the hinge pipeline. */
 int rgc_sync_spectrum_particles(const rgc_particles_t* p, size_t nactive,
                                 const float* bins_e_syn, size_t nbins, const float* tab_x,
                                 const float* tab_y, size_t tab_n, float B0, float g_syn,

@@ -72,11 +72,11 @@ namespace rgb {
       throw std::runtime_error("bins_e_syn must be in units of mc^2");
     }
     std::vector<real_t> spec(nbins, 0.0f);
-    if (prtls.is_allocated()) { // nactive == 0 still joins a multi-rank all-reduce
-      check(rgc_sync_spectrum_particles(prtls.handle(), prtls.nactive(), bins_e_syn.host_data(),
-                                        nbins, tab.x.data(), tab.y.data(), tab.x.size(), B0,
-                                        g_syn, e_syn_at_g_syn, spec.data(), nullptr));
-    }
+    // unallocated particles are an empty shard: the call still joins a multi-rank all-reduce
+    const bool alloc = prtls.is_allocated();
+    check(rgc_sync_spectrum_particles(alloc ? prtls.handle() : nullptr, alloc ? prtls.nactive() : 0,
+                                      bins_e_syn.host_data(), nbins, tab.x.data(), tab.y.data(),
+                                      tab.x.size(), B0, g_syn, e_syn_at_g_syn, spec.data(), nullptr));
     py::print(": OK", "flush"_a = true);
     return Array1D<real_t> { spec };
   }

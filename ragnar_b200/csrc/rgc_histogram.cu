@@ -483,7 +483,7 @@ extern "C" {
     const std::size_t off_binfo  = 0;
     const std::size_t off_counts = align(off_binfo + n * sizeof(float4));
     const std::size_t off_wfx    = off_counts + n * 8; // adjacent: one u64 all-reduce of 2n
-    const std::size_t off_wslow  = align(off_wfx + n * 8);
+    const std::size_t off_wslow  = off_wfx + n * 8;     // adjacent too: [counts | wfx | wslow] is one exchange
     const std::size_t off_clamp  = align(off_wslow + n * 8);
     const std::size_t total      = off_clamp + (std::size_t)nctas * 2 * sizeof(double);
     void*             scratch    = nullptr;
@@ -511,16 +511,12 @@ extern "C" {
     hist_fold_clamp_kernel<<<1, 32, 0, c.stream>>>(P.clamp_part, nctas, P.wslow, (int)n);
     RGC_CUDA(cudaGetLastError());
     count_launch(1);
-    if (c.nccl_comm && c.nranks > 1) {
-      RGC_TRY(allreduce_group_begin());
-      RGC_TRY(allreduce_sum_u64(P.counts, 2 * n));
-      RGC_TRY(allreduce_sum_f64(P.wslow, n));
-      RGC_TRY(allreduce_group_end());
-    }
+    RGC_TRY(allreduce_sum_mixed(P.counts, 2 * n, n));
     std::vector<unsigned char> raw(off_clamp - off_counts);
     RGC_CUDA(cudaMemcpyAsync(raw.data(), sbase + off_counts, raw.size(), cudaMemcpyDeviceToHost,
                              c.stream));
     RGC_CUDA(cudaStreamSynchronize(c.stream));
+    RGC_TRY(exchange_check());
     const auto* counts = reinterpret_cast<const unsigned long long*>(raw.data());
     const auto* wfx    = reinterpret_cast<const unsigned long long*>(raw.data() + (off_wfx - off_counts));
     const auto* wslow  = reinterpret_cast<const double*>(raw.data() + (off_wslow - off_counts));

@@ -51,7 +51,7 @@ namespace rgc {
 
   // ----------------------------------------------------------------- context
   constexpr std::size_t kStageBytes = std::size_t(32) << 20; // per pinned stage
-  constexpr int         kNumStages  = 2;
+  constexpr int         kNumStages  = 4;
 
   struct Context {
     bool         initialized { false };
@@ -61,8 +61,8 @@ namespace rgc {
     cudaStream_t stream { nullptr };      // compute + ordered copies
     cudaStream_t copy_stream { nullptr }; // bulk H2D of particle columns
     // pinned staging ring for pageable host sources
-    void*       stage[kNumStages] { nullptr, nullptr };
-    cudaEvent_t stage_free[kNumStages] { nullptr, nullptr };
+    void*       stage[kNumStages] {};
+    cudaEvent_t stage_free[kNumStages] {};
     // event pair for rgc_last_kernel_ms
     cudaEvent_t ev[6] { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     float       last_ms[4] { 0.f, 0.f, 0.f, 0.f }; // total, dominant kernel, prologue kernel, sort
@@ -94,9 +94,11 @@ namespace rgc {
   // all-reduce (sum) in place on the compute stream; no-op without a communicator
   int allreduce_sum_f64(double* dev, std::size_t n);
   int allreduce_sum_u64(unsigned long long* dev, std::size_t n);
-  // ncclGroupStart / ncclGroupEnd around several all-reduces: one fused launch
-  int allreduce_group_begin();
-  int allreduce_group_end();
+  // [n_u64 unsigned 64-bit | n_f64 doubles], contiguous: ONE exchange kernel (or one NCCL group)
+  int allreduce_sum_mixed(void* dev, std::size_t n_u64, std::size_t n_f64);
+  // after the stream synchronisation that follows an all-reduce: RGC_ERR_NCCL when a peer
+  // never delivered its partial result within RGC_XCHG_TIMEOUT_MS (the result is poisoned)
+  int exchange_check();
 
   // frees the pinned I/O lanes of the HDF5 streaming reader (rgc_tristan.cpp)
   void io_release_lanes();

@@ -18,8 +18,11 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <new>
+#include <thread>
 
 namespace rgc {
 
@@ -99,9 +102,103 @@ namespace rgc {
     return attr.type == cudaMemoryTypeHost;
   }
 
+  // Worker threads that fill a pinned stage from a pageable source in parallel slices: one
+  // thread moves ~10 GB/s, a PCIe 5 x16 link takes ~55 GB/s.  RGC_COPY_THREADS (default 8,
+  // at most half the hardware threads) sets the width; created on first use, joined in
+  // rgc_finalize.
+  class CopyPool {
+  public:
+    explicit CopyPool(int n) {
+      for (int i = 0; i < n; ++i) {
+        workers_.emplace_back([this, i] { loop(i); });
+      }
+    }
+    ~CopyPool() {
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        stop_ = true;
+      }
+      start_.notify_all();
+      for (auto& t : workers_) {
+        t.join();
+      }
+    }
+    void copy(void* dst, const void* src, std::size_t bytes) {
+      std::unique_lock<std::mutex> lk(m_);
+      dst_     = static_cast<char*>(dst);
+      src_     = static_cast<const char*>(src);
+      bytes_   = bytes;
+      pending_ = (int)workers_.size();
+      ++gen_;
+      start_.notify_all();
+      done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+  private:
+    void loop(int id) {
+      std::uint64_t seen = 0;
+      for (;;) {
+        std::unique_lock<std::mutex> lk(m_);
+        start_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) {
+          return;
+        }
+        seen = gen_;
+        char*             d = dst_;
+        const char*       s = src_;
+        const std::size_t b = bytes_;
+        const std::size_t n = workers_.size();
+        lk.unlock();
+        const std::size_t per = (((b + n - 1) / n) + 4095) & ~std::size_t(4095);
+        const std::size_t off = (std::size_t)id * per;
+        if (off < b) {
+          std::memcpy(d + off, s + off, std::min(per, b - off));
+        }
+        lk.lock();
+        if (--pending_ == 0) {
+          done_.notify_one();
+        }
+      }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex               m_;
+    std::condition_variable  start_, done_;
+    std::uint64_t            gen_ { 0 };
+    int                      pending_ { 0 };
+    bool                     stop_ { false };
+    char*                    dst_ { nullptr };
+    const char*              src_ { nullptr };
+    std::size_t              bytes_ { 0 };
+  };
+
+  static CopyPool*  g_copy_pool = nullptr;
+  static std::mutex g_stage_mutex; // the pinned ring and the pool serve one copy at a time
+  static int        g_next_stage = 0;
+
+  static CopyPool* copy_pool() {
+    if (!g_copy_pool) {
+      int n = 8;
+      if (const char* s = std::getenv("RGC_COPY_THREADS")) {
+        n = std::atoi(s);
+      }
+      const int hw = (int)std::thread::hardware_concurrency();
+      n = std::max(1, std::min(n, std::max(1, hw / 2)));
+      g_copy_pool = new CopyPool(n);
+    }
+    return g_copy_pool;
+  }
+
+  void copy_pool_release() {
+    std::lock_guard<std::mutex> lk(g_stage_mutex);
+    delete g_copy_pool;
+    g_copy_pool = nullptr;
+  }
+
   // Pinned sources go out as ONE async DMA (caller keeps them alive until the
-  // stream is synchronised); pageable sources are memcpy'd chunk-wise into a
-  // two-deep pinned ring so the CPU copy of chunk k+1 overlaps the DMA of chunk k.
+  // stream is synchronised); pageable sources are copied chunk-wise into a ring of
+  // pinned stages (large chunks by the worker pool above) so the CPU copy of chunk
+  // k+1 overlaps the DMA of chunk k.  The ring position persists between calls, so a
+  // run of small copies does not wait for the previous one's DMA.
   int copy_h2d(void* dst, const void* src, std::size_t bytes, cudaStream_t stream) {
     if (bytes == 0) {
       return RGC_OK;
@@ -110,19 +207,24 @@ namespace rgc {
       RGC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
       return RGC_OK;
     }
+    std::lock_guard<std::mutex> lk(g_stage_mutex);
     RGC_TRY(ensure_stages());
     auto&       c    = ctx();
     std::size_t done = 0;
-    int         s    = 0;
     while (done < bytes) {
+      const int         s     = g_next_stage;
       const std::size_t chunk = bytes - done < kStageBytes ? bytes - done : kStageBytes;
       RGC_CUDA(cudaEventSynchronize(c.stage_free[s]));
-      std::memcpy(c.stage[s], static_cast<const char*>(src) + done, chunk);
+      if (chunk >= (std::size_t(4) << 20)) {
+        copy_pool()->copy(c.stage[s], static_cast<const char*>(src) + done, chunk);
+      } else {
+        std::memcpy(c.stage[s], static_cast<const char*>(src) + done, chunk);
+      }
       RGC_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + done, c.stage[s], chunk,
                                cudaMemcpyHostToDevice, stream));
       RGC_CUDA(cudaEventRecord(c.stage_free[s], stream));
       done += chunk;
-      s = (s + 1) % kNumStages;
+      g_next_stage = (s + 1) % kNumStages;
     }
     return RGC_OK;
   }
@@ -209,14 +311,25 @@ namespace rgc {
     unsigned long long* peer[kXchgMaxRanks];
     int                 rank, nranks;
     unsigned long long  seq;
-    unsigned long long* data; // in / out, n elements
-    int                 n;
-    int                 is_f64;
+    unsigned long long* data; // in / out, n elements: [0, n_u64) summed as u64, the rest as f64
+    int                 n, n_u64;
+    unsigned long long  timeout_ns;
+    int*                status; // host-mapped word: 1 + rank of a peer that never arrived
   };
 
+  __device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+  }
+
   __global__ void __launch_bounds__(256) xchg_allreduce_kernel(const XchgParams P) {
+    __shared__ int    s_late;
     const std::size_t set_off  = (P.seq & 1ull) * (kXchgSetBytes / 8);
     const std::size_t flag_off = set_off + (std::size_t)kXchgMaxRanks * kXchgSlot;
+    if (threadIdx.x == 0) {
+      s_late = 0;
+    }
     // 1. my vector into slot `rank` of every rank
     for (int p = 0; p < P.nranks; ++p) {
       unsigned long long* dst = P.peer[p] + set_off + (std::size_t)P.rank * kXchgSlot;
@@ -226,24 +339,42 @@ namespace rgc {
     }
     __threadfence_system();
     __syncthreads();
-    // 2. raise my flag everywhere, wait for everyone's flag here
+    // 2. raise my flag everywhere, wait for everyone's flag here.  The wait is bounded in
+    // TIME (RGC_XCHG_TIMEOUT_MS, default 10 min — a peer may legitimately sit in a cold
+    // disk read): on expiry nothing is summed, the result is poisoned and the host-visible
+    // status word makes the calling entry point fail with RGC_ERR_NCCL.
     if (threadIdx.x < P.nranks) {
       unsigned long long* f = P.peer[threadIdx.x] + flag_off + (std::size_t)P.rank * 16;
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(P.seq) : "memory");
       const unsigned long long* mine = P.peer[P.rank] + flag_off + (std::size_t)threadIdx.x * 16;
       unsigned long long        v    = 0;
-      for (long long spin = 0; spin < (1ll << 24); ++spin) { // bounded: a dead peer must not hang the GPU
+      const unsigned long long  t0   = global_timer_ns();
+      for (unsigned spin = 0;; ++spin) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
         if (v >= P.seq) {
+          break;
+        }
+        if ((spin & 255u) == 255u && global_timer_ns() - t0 > P.timeout_ns) {
+          atomicMax(&s_late, 1 + (int)threadIdx.x);
           break;
         }
       }
     }
     __syncthreads();
+    if (s_late != 0) {
+      if (threadIdx.x == 0) {
+        *reinterpret_cast<volatile int*>(P.status) = s_late;
+        __threadfence_system();
+      }
+      for (int i = threadIdx.x; i < P.n; i += blockDim.x) {
+        P.data[i] = i < P.n_u64 ? ~0ull : 0x7ff8000000000000ull; // never a plausible partial sum
+      }
+      return;
+    }
     // 3. sum the slots in rank order
     const unsigned long long* src = P.peer[P.rank] + set_off;
     for (int i = threadIdx.x; i < P.n; i += blockDim.x) {
-      if (P.is_f64) {
+      if (i >= P.n_u64) {
         double s = 0.0;
         for (int r = 0; r < P.nranks; ++r) {
           s += __longlong_as_double((long long)src[(std::size_t)r * kXchgSlot + i]);
@@ -259,65 +390,153 @@ namespace rgc {
     }
   }
 
-  static int xchg_allreduce(void* dev, std::size_t n, bool is_f64) {
-    auto&      c = ctx();
+  static int* g_xchg_status_host = nullptr; // cudaHostAlloc'ed (mapped), written by the kernel on timeout
+  static int* g_xchg_status_dev  = nullptr;
+  static bool g_xchg_broken      = false;
+
+  static unsigned long long xchg_timeout_ns() {
+    if (const char* s = std::getenv("RGC_XCHG_TIMEOUT_MS")) {
+      const long long ms = std::atoll(s);
+      if (ms > 0) {
+        return (unsigned long long)ms * 1000000ull;
+      }
+    }
+    return 600ull * 1000000000ull;
+  }
+
+  static int xchg_allreduce(void* dev, std::size_t n_u64, std::size_t n_f64) {
+    auto& c = ctx();
+    if (g_xchg_broken) {
+      return fail(RGC_ERR_NCCL, "the peer-store exchange timed out earlier; destroy and re-create the "
+                                "communicator (rgc_comm_destroy / rgc_comm_init)");
+    }
     XchgParams P {};
     for (int r = 0; r < c.nranks; ++r) {
       P.peer[r] = static_cast<unsigned long long*>(c.xchg_peer[r]);
     }
-    P.rank   = c.rank;
-    P.nranks = c.nranks;
-    P.seq    = ++c.xchg_seq;
-    P.data   = static_cast<unsigned long long*>(dev);
-    P.n      = (int)n;
-    P.is_f64 = is_f64 ? 1 : 0;
+    P.rank       = c.rank;
+    P.nranks     = c.nranks;
+    P.seq        = ++c.xchg_seq;
+    P.data       = static_cast<unsigned long long*>(dev);
+    P.n          = (int)(n_u64 + n_f64);
+    P.n_u64      = (int)n_u64;
+    P.timeout_ns = xchg_timeout_ns();
+    P.status     = g_xchg_status_dev;
     xchg_allreduce_kernel<<<1, 256, 0, c.stream>>>(P);
     RGC_CUDA(cudaGetLastError());
     count_launch(1);
     return RGC_OK;
   }
 
+  // after the caller's stream synchronisation: did an exchange of this call time out?
+  int exchange_check() {
+    if (!g_xchg_status_host) {
+      return RGC_OK;
+    }
+    const int late = *reinterpret_cast<volatile int*>(g_xchg_status_host);
+    if (late == 0) {
+      return RGC_OK;
+    }
+    *g_xchg_status_host = 0;
+    g_xchg_broken       = true;
+    return fail(RGC_ERR_NCCL,
+                "all-reduce over the peer-store exchange timed out: rank %d never delivered its "
+                "partial result (RGC_XCHG_TIMEOUT_MS); the result of this call is invalid",
+                late - 1);
+  }
+
+  static void xchg_release(void* local) {
+    auto& c = ctx();
+    for (int r = 0; r < kXchgMaxRanks; ++r) {
+      if (c.xchg_peer[r] && c.xchg_peer[r] != local) {
+        cudaIpcCloseMemHandle(c.xchg_peer[r]);
+      }
+      c.xchg_peer[r] = nullptr;
+    }
+    if (local) {
+      cudaFree(local);
+    }
+    if (g_xchg_status_host) {
+      cudaFreeHost(g_xchg_status_host);
+      g_xchg_status_host = nullptr;
+      g_xchg_status_dev  = nullptr;
+    }
+    cudaGetLastError();
+  }
+
   // maps every rank's exchange buffer into this process (CUDA IPC; handles travel through
-  // one ncclAllGather).  Any failure leaves xchg_ready false: NCCL carries the exchange.
+  // one ncclAllGather).  EVERY rank takes part in both collectives below whatever happened
+  // locally (RGC_XCHG=0, a failed allocation, a handle that does not open): a local failure
+  // travels as ok = 0 in the gathered record / the reduced verdict, and all ranks then agree
+  // on NCCL.  Nothing is leaked on any path.
   static int xchg_setup() {
     auto& c = ctx();
-    c.xchg_ready = false;
-    const char* env = std::getenv("RGC_XCHG"); // "0": always NCCL
-    if ((env && env[0] == '0') || c.nranks < 2 || c.nranks > kXchgMaxRanks) {
+    c.xchg_ready  = false;
+    g_xchg_broken = false;
+    if (c.nranks < 2 || c.nranks > kXchgMaxRanks) { // the same on every rank
       return RGC_OK;
     }
-    void* local = nullptr;
-    if (cudaMalloc(&local, kXchgBytes) != cudaSuccess) {
-      cudaGetLastError();
-      return RGC_OK;
-    }
-    cudaMemset(local, 0, kXchgBytes);
-    cudaDeviceSynchronize();
+    const char* env = std::getenv("RGC_XCHG"); // "0": always NCCL (may differ between ranks)
+    bool        ok  = !(env && env[0] == '0');
+    void*       local = nullptr;
     cudaIpcMemHandle_t mine;
-    bool               ok = cudaIpcGetMemHandle(&mine, local) == cudaSuccess;
-    // all-gather the handles (and whether every rank got this far)
-    unsigned char* dbuf = nullptr;
-    const std::size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
-    if (cudaMalloc(reinterpret_cast<void**>(&dbuf), rec * c.nranks) != cudaSuccess) {
-      cudaGetLastError();
-      cudaFree(local);
-      return RGC_OK;
+    std::memset(&mine, 0, sizeof(mine));
+    if (ok) {
+      ok = cudaMalloc(&local, kXchgBytes) == cudaSuccess;
+      if (!ok) {
+        local = nullptr;
+      }
     }
+    if (ok) {
+      ok = cudaMemset(local, 0, kXchgBytes) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess &&
+           cudaIpcGetMemHandle(&mine, local) == cudaSuccess;
+    }
+    if (ok) {
+      ok = cudaHostAlloc(reinterpret_cast<void**>(&g_xchg_status_host), 64, cudaHostAllocMapped) == cudaSuccess;
+      if (ok) {
+        *g_xchg_status_host = 0;
+        ok = cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_xchg_status_dev), g_xchg_status_host, 0) ==
+             cudaSuccess;
+      } else {
+        g_xchg_status_host = nullptr;
+      }
+    }
+    cudaGetLastError();
+    // ---- collective 1: all-gather {handle, ok}; the buffer comes from the context's
+    // scratch (no rank-local early exit between here and the verdict)
+    const std::size_t rec     = sizeof(cudaIpcMemHandle_t) + 8;
+    void*             scratch = nullptr;
+    int               rc      = ensure_scratch(rec * c.nranks + 64, &scratch);
+    if (rc != RGC_OK) {
+      xchg_release(local);
+      return rc;
+    }
+    unsigned char* dbuf = static_cast<unsigned char*>(scratch);
+    int*           dflag = reinterpret_cast<int*>(dbuf + ((rec * c.nranks + 15) & ~std::size_t(15)));
     std::vector<unsigned char> hbuf(rec * c.nranks, 0);
     std::memcpy(hbuf.data() + rec * c.rank, &mine, sizeof(mine));
     hbuf[rec * c.rank + sizeof(mine)] = ok ? 1 : 0;
-    RGC_CUDA(cudaMemcpy(dbuf + rec * c.rank, hbuf.data() + rec * c.rank, rec, cudaMemcpyHostToDevice));
-    RGC_NCCL(nccl().AllGather(dbuf + rec * c.rank, dbuf, rec, ncclChar,
-                              static_cast<ncclComm_t>(c.nccl_comm), c.stream));
-    RGC_CUDA(cudaStreamSynchronize(c.stream));
-    RGC_CUDA(cudaMemcpy(hbuf.data(), dbuf, rec * c.nranks, cudaMemcpyDeviceToHost));
-    cudaFree(dbuf);
+    auto bail = [&](int code) {
+      xchg_release(local);
+      return code;
+    };
+    if (cudaMemcpy(dbuf + rec * c.rank, hbuf.data() + rec * c.rank, rec, cudaMemcpyHostToDevice) != cudaSuccess) {
+      return bail(fail(RGC_ERR_CUDA, "exchange setup: cudaMemcpy failed: %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    ncclResult_t nr = nccl().AllGather(dbuf + rec * c.rank, dbuf, rec, ncclChar,
+                                       static_cast<ncclComm_t>(c.nccl_comm), c.stream);
+    if (nr != ncclSuccess) {
+      return bail(fail(RGC_ERR_NCCL, "exchange setup: ncclAllGather failed: %s", nccl().GetErrorString(nr)));
+    }
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess ||
+        cudaMemcpy(hbuf.data(), dbuf, rec * c.nranks, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      return bail(fail(RGC_ERR_CUDA, "exchange setup: %s", cudaGetErrorString(cudaGetLastError())));
+    }
     for (int r = 0; r < c.nranks; ++r) {
       ok = ok && hbuf[rec * r + sizeof(mine)] == 1;
     }
-    int opened = 0;
     if (ok) {
-      for (int r = 0; r < c.nranks && ok; ++r) {
+      for (int r = 0; r < c.nranks; ++r) {
         if (r == c.rank) {
           c.xchg_peer[r] = local;
           continue;
@@ -331,34 +550,29 @@ namespace rgc {
           break;
         }
         c.xchg_peer[r] = ptr;
-        ++opened;
       }
     }
-    // every rank must agree before anyone stores into a peer: all-reduce the verdict
-    // (this is also the barrier behind the memsets above)
-    int* dflag = nullptr;
-    RGC_CUDA(cudaMalloc(reinterpret_cast<void**>(&dflag), sizeof(int)));
-    const int mine_ok = ok ? 0 : 1;
-    RGC_CUDA(cudaMemcpy(dflag, &mine_ok, sizeof(int), cudaMemcpyHostToDevice));
-    RGC_NCCL(nccl().AllReduce(dflag, dflag, 1, ncclInt32, ncclSum, static_cast<ncclComm_t>(c.nccl_comm),
-                              c.stream));
-    RGC_CUDA(cudaStreamSynchronize(c.stream));
+    // ---- collective 2: every rank must agree before anyone stores into a peer (this is
+    // also the barrier behind the memsets above)
+    const int mine_bad = ok ? 0 : 1;
+    if (cudaMemcpy(dflag, &mine_bad, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+      return bail(fail(RGC_ERR_CUDA, "exchange setup: cudaMemcpy failed: %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    nr = nccl().AllReduce(dflag, dflag, 1, ncclInt32, ncclSum, static_cast<ncclComm_t>(c.nccl_comm), c.stream);
+    if (nr != ncclSuccess) {
+      return bail(fail(RGC_ERR_NCCL, "exchange setup: ncclAllReduce failed: %s", nccl().GetErrorString(nr)));
+    }
     int failed = 1;
-    RGC_CUDA(cudaMemcpy(&failed, dflag, sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(dflag);
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess ||
+        cudaMemcpy(&failed, dflag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      return bail(fail(RGC_ERR_CUDA, "exchange setup: %s", cudaGetErrorString(cudaGetLastError())));
+    }
     if (failed != 0) {
-      for (int r = 0; r < c.nranks; ++r) {
-        if (r != c.rank && c.xchg_peer[r]) {
-          cudaIpcCloseMemHandle(c.xchg_peer[r]);
-        }
-        c.xchg_peer[r] = nullptr;
-      }
-      cudaFree(local);
+      xchg_release(local); // NCCL carries the exchange on every rank
       return RGC_OK;
     }
     c.xchg_seq   = 0;
     c.xchg_ready = true;
-    (void)opened;
     return RGC_OK;
   }
 
@@ -368,62 +582,36 @@ namespace rgc {
       return;
     }
     cudaStreamSynchronize(c.stream);
-    for (int r = 0; r < c.nranks; ++r) {
-      if (c.xchg_peer[r]) {
-        if (r == c.rank) {
-          cudaFree(c.xchg_peer[r]);
-        } else {
-          cudaIpcCloseMemHandle(c.xchg_peer[r]);
-        }
-        c.xchg_peer[r] = nullptr;
-      }
-    }
+    xchg_release(c.xchg_peer[c.rank]);
     c.xchg_ready = false;
   }
 
-  int allreduce_sum_f64(double* dev, std::size_t n) {
+  // in-place sum over ranks of [n_u64 unsigned 64-bit | n_f64 doubles], contiguous
+  int allreduce_sum_mixed(void* dev, std::size_t n_u64, std::size_t n_f64) {
     auto& c = ctx();
-    if (!c.nccl_comm || c.nranks <= 1 || n == 0) {
+    if (!c.nccl_comm || c.nranks <= 1 || n_u64 + n_f64 == 0) {
       return RGC_OK;
     }
-    if (c.xchg_ready && n <= kXchgSlot) {
-      return xchg_allreduce(dev, n, true);
+    if (c.xchg_ready && n_u64 + n_f64 <= kXchgSlot) {
+      return xchg_allreduce(dev, n_u64, n_f64);
     }
-    RGC_NCCL(nccl().AllReduce(dev, dev, n, ncclFloat64, ncclSum,
-                              static_cast<ncclComm_t>(c.nccl_comm), c.stream));
-    return RGC_OK;
-  }
-
-  int allreduce_sum_u64(unsigned long long* dev, std::size_t n) {
-    auto& c = ctx();
-    if (!c.nccl_comm || c.nranks <= 1 || n == 0) {
-      return RGC_OK;
-    }
-    if (c.xchg_ready && n <= kXchgSlot) {
-      return xchg_allreduce(dev, n, false);
-    }
-    RGC_NCCL(nccl().AllReduce(dev, dev, n, ncclUint64, ncclSum,
-                              static_cast<ncclComm_t>(c.nccl_comm), c.stream));
-    return RGC_OK;
-  }
-
-  int allreduce_group_begin() {
-    auto& c = ctx();
-    if (!c.nccl_comm || c.nranks <= 1) {
-      return RGC_OK;
-    }
+    auto* base = static_cast<unsigned long long*>(dev);
     RGC_NCCL(nccl().GroupStart());
-    return RGC_OK;
-  }
-
-  int allreduce_group_end() {
-    auto& c = ctx();
-    if (!c.nccl_comm || c.nranks <= 1) {
-      return RGC_OK;
+    if (n_u64) {
+      RGC_NCCL(nccl().AllReduce(base, base, n_u64, ncclUint64, ncclSum, static_cast<ncclComm_t>(c.nccl_comm),
+                                c.stream));
+    }
+    if (n_f64) {
+      RGC_NCCL(nccl().AllReduce(base + n_u64, base + n_u64, n_f64, ncclFloat64, ncclSum,
+                                static_cast<ncclComm_t>(c.nccl_comm), c.stream));
     }
     RGC_NCCL(nccl().GroupEnd());
     return RGC_OK;
   }
+
+  int allreduce_sum_f64(double* dev, std::size_t n) { return allreduce_sum_mixed(dev, 0, n); }
+
+  int allreduce_sum_u64(unsigned long long* dev, std::size_t n) { return allreduce_sum_mixed(dev, n, 0); }
 
 } // namespace rgc
 
@@ -510,6 +698,7 @@ extern "C" {
     rgc_comm_destroy();
     io_release_lanes();
     pair_release_plans();
+    copy_pool_release();
     for (int s = 0; s < kNumStages; ++s) {
       if (c.stage[s]) {
         cudaFreeHost(c.stage[s]);

@@ -648,6 +648,9 @@ namespace rgc {
                              cudaMemcpyDeviceToHost, c.stream));
     RGC_CUDA(cudaEventRecord(c.ev[1], c.stream));
     RGC_CUDA(cudaStreamSynchronize(c.stream));
+    if (allreduce) {
+      RGC_TRY(exchange_check());
+    }
     std::copy(back.begin(), back.begin() + nbins, acc_host.begin());
     {
       unsigned long long le = 0;
@@ -695,10 +698,13 @@ extern "C" {
                                   const float* tab_y, size_t tab_n, float B0, float g_syn,
                                   float e_syn_at_g_syn, float* out_spec, double* out_spec64) {
     RGC_REQUIRE_INIT();
-    if (!p || !p->allocated) {
+    // an unallocated container is an empty shard (the reference launches 0 x M threads over
+    // empty Views): it still joins a multi-rank all-reduce, so no rank is left waiting
+    const bool empty = (!p || !p->allocated) && nactive == 0;
+    if (!empty && (!p || !p->allocated)) {
       return fail(RGC_ERR_INVALID, "Particles not allocated");
     }
-    if (nactive > p->nalloc) {
+    if (!empty && nactive > p->nalloc) {
       return fail(RGC_ERR_INVALID, "nactive %zu exceeds allocation %zu", nactive, p->nalloc);
     }
     SpectrumSource src;

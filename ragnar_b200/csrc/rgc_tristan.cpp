@@ -38,6 +38,7 @@ namespace {
 
   struct LanePool {
     std::mutex mtx;
+    std::mutex in_use; // held for a whole stream_to_device call: the lanes serve one reader at a time
     Lane       lanes[kMaxThreads];
     int        ready { 0 };
   };
@@ -102,6 +103,9 @@ namespace {
       return RGC_OK;
     }
     const int nthr = (int)std::min<std::size_t>((std::size_t)io_threads(), slabs.size());
+    // a prefetching reader thread and a main-thread read may arrive together: the second
+    // one waits here instead of sharing staging slots with the first
+    std::lock_guard<std::mutex> one_reader(pool().in_use);
     RGC_TRY(ensure_lanes(nthr));
     std::atomic<std::size_t> next { 0 };
     std::atomic<bool>        failed { false };

@@ -99,6 +99,45 @@ if rank == 0:
 dist.barrier()
 if rank == 0:
     shutil.rmtree(root, ignore_errors=True)
+# ---- a starved exchange must fail loudly, never return a partial sum: the last rank
+# arrives 3 s late at a call whose exchange waits 300 ms at most
+if cabi.comm_exchange_kind().startswith("peer-store"):
+    import time
+
+    os.environ["RGC_XCHG_TIMEOUT_MS"] = "300"
+    dist.barrier()
+    late = rank == world - 1
+    if late:
+        time.sleep(3.0)
+    try:
+        got = cabi.sync_spectrum_particles(p, bins, *consts)[1]
+        raised = False
+    except RuntimeError as e:
+        raised = "timed out" in str(e)
+        got = None
+    # early ranks must raise; the late rank finds every peer's data in place and gets the full sum
+    ok_t = raised if not late else (got is not None and np.array_equal(got, spec))
+    t = torch.tensor([0 if ok_t else 1], device="cuda")
+    dist.all_reduce(t)
+    # afterwards the exchange refuses further calls until the communicator is re-created
+    refused = True
+    if not late:
+        try:
+            cabi.sync_spectrum_particles(p, bins, *consts)
+            refused = False
+        except RuntimeError:
+            pass
+    dist.barrier()
+    os.environ.pop("RGC_XCHG_TIMEOUT_MS")
+    cabi.comm_destroy()
+    rdist.install_communicator(cabi, dist)
+    again = cabi.sync_spectrum_particles(p, bins, *consts)[1]
+    ok_t2 = int(t.item()) == 0 and refused and np.array_equal(again, spec)
+    if rank == 0:
+        print(f"[dist_check] world={world} starved exchange: early ranks raised RGC_ERR_NCCL, late rank "
+              f"summed, exchange refused until re-created, result after re-creation bit-identical -> "
+              f"{'OK' if ok_t2 else 'FAIL'}", flush=True)
+    ok = ok and ok_t2
 flag = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(flag)
 dist.barrier()
