@@ -76,6 +76,11 @@ const char* rgc_last_error(void);
 /* number of kernels this library has launched since rgc_init (bench evidence) */
 uint64_t rgc_launch_count(void);
 
+/* Particle columns are allocated from the device's stream-ordered memory pool and stay cached
+ * there when a container is released (re-creating a container per species / step then costs
+ * no cudaMalloc / cudaFree); this returns the cached blocks to the device. */
+int rgc_trim_memory(void);
+
 /* pinned host memory for zero-staging H2D/D2H (cudaHostAlloc / cudaFreeHost) */
 int rgc_host_alloc(size_t bytes, void** ptr);
 int rgc_host_free(void* ptr);
@@ -245,6 +250,10 @@ int rgc_last_kernel_times(float* ms, int n);
  * all beyond the table's zero tail for a bucket are skipped, so this is <= the
  * particles x bins of the call rounded up to whole groups (roofline accounting). */
 int rgc_last_pair_lane_evals(double* lane_evals);
+/* (particle, bin) pairs of the last rgc_sync_spectrum_particles call on this rank whose table
+ * cell pair is not identically zero — what an ideal kernel would have to evaluate (the
+ * whole-step roofline of bench.py); counted on the device by pair_moments_kernel. */
+int rgc_last_pair_ontable_evals(double* evals);
 
 /* Roofline denominators measured on the device, on the compute stream (bench
  * harness only; MEASURED_PEAKS.json has no FP32 / shared-memory entry).

@@ -117,6 +117,8 @@ class _Port:
             lib.orc_plaw_norm.restype = ctypes.c_float
             lib.orc_plaw_norm.argtypes = [ctypes.c_float] * 3
             lib.orc_num_threads.restype = ctypes.c_int
+            lib.orc_set_num_threads.argtypes = [ctypes.c_int]
+            lib.orc_set_num_threads.restype = None
             for name in ("orc_logspace", "orc_linspace"):
                 getattr(lib, name).argtypes = [ctypes.c_float, ctypes.c_float,
                                                ctypes.c_size_t, _f32p]
@@ -256,6 +258,11 @@ class _Port:
 
     def num_threads(self) -> int:
         return int(self.lib.orc_num_threads())
+
+    def set_num_threads(self, n: int) -> int:
+        """OpenMP width of the oracle AND of oracle/_ref (one libgomp per process)."""
+        self.lib.orc_set_num_threads(int(n))
+        return self.num_threads()
 
 
 port = _Port()

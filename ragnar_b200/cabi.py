@@ -77,7 +77,9 @@ SIGNATURES = {
                                   _f32p, _f64p]),
     "rgc_last_kernel_ms": (C.c_int, [_f32p]),
     "rgc_last_kernel_times": (C.c_int, [_f32p, C.c_int]),
+    "rgc_trim_memory": (C.c_int, []),
     "rgc_last_pair_lane_evals": (C.c_int, [_f64p]),
+    "rgc_last_pair_ontable_evals": (C.c_int, [_f64p]),
     "rgc_comm_exchange_kind": (C.c_int, [C.POINTER(C.c_int)]),
     "rgc_measure_peak": (C.c_int, [C.c_int, _f64p, _f64p]),
     "rgc_h5_open": (C.c_int, [C.c_char_p, C.c_int, _vpp]),
@@ -190,6 +192,18 @@ def comm_exchange_kind() -> str:
     k = C.c_int()
     check(lib().rgc_comm_exchange_kind(C.byref(k)))
     return {0: "single rank", 1: "ncclAllReduce", 2: "peer-store exchange over NVLink"}[k.value]
+
+
+def trim_memory() -> None:
+    """return the cached (released) particle columns to the device"""
+    check(lib().rgc_trim_memory())
+
+
+def last_pair_ontable_evals() -> float:
+    """pairs of the last hinge launch that are on the F table (call right after the spectrum)"""
+    v = C.c_double()
+    check(lib().rgc_last_pair_ontable_evals(C.byref(v)))
+    return float(v.value)
 
 
 def last_pair_lane_evals() -> float:

@@ -67,6 +67,7 @@ namespace rgc {
     cudaEvent_t ev[6] { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     float       last_ms[4] { 0.f, 0.f, 0.f, 0.f }; // total, dominant kernel, prologue kernel, sort
     double      last_lane_evals { 0.0 }; // hinge evaluations the pair kernel issued in the last call
+    double      last_ontable_evals { 0.0 }; // pairs of that call on a non-zero cell pair of the table
     // NCCL (dlopen'ed lazily)
     void* nccl_comm { nullptr };
     int   rank { 0 };

@@ -12,6 +12,7 @@
 #include "rgc_internal.hpp"
 
 #include <dlfcn.h>
+#include <immintrin.h>
 #include <execinfo.h>
 #include <csignal>
 #include <nccl.h> // types and enum values only; the library is dlopen'ed
@@ -103,9 +104,40 @@ namespace rgc {
   }
 
   // Worker threads that fill a pinned stage from a pageable source in parallel slices: one
-  // thread moves ~10 GB/s, a PCIe 5 x16 link takes ~55 GB/s.  RGC_COPY_THREADS (default 8,
-  // at most half the hardware threads) sets the width; created on first use, joined in
-  // rgc_finalize.
+  // thread moves 4-10 GB/s, a PCIe 5 x16 link takes ~55 GB/s (measured on the bench box:
+  // 4 / 8 / 16 threads -> 31 / 32 / 51 GB/s end to end).  RGC_COPY_THREADS sets the width
+  // (default: the hardware threads divided by the ranks on the node); created on first
+  // use, joined in rgc_finalize.
+  // memcpy into a pinned stage with non-temporal stores: the destination is read next by the
+  // DMA engine, never by this core, so the read-for-ownership of a cached store (a third of
+  // the host memory traffic of the copy) is skipped.  dst must be 32-byte aligned.
+  __attribute__((target("avx2"))) static void stream_copy_avx2(char* dst, const char* src, std::size_t bytes) {
+    std::size_t i = 0;
+    for (; i + 128 <= bytes; i += 128) {
+      const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+      const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
+      const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
+      const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
+      _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
+      _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), b);
+      _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), c);
+      _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), d);
+    }
+    _mm_sfence();
+    if (i < bytes) {
+      std::memcpy(dst + i, src + i, bytes - i);
+    }
+  }
+
+  static void stage_copy(char* dst, const char* src, std::size_t bytes) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2 && (reinterpret_cast<std::uintptr_t>(dst) & 31u) == 0 && bytes >= 4096) {
+      stream_copy_avx2(dst, src, bytes);
+    } else {
+      std::memcpy(dst, src, bytes);
+    }
+  }
+
   class CopyPool {
   public:
     explicit CopyPool(int n) {
@@ -152,7 +184,7 @@ namespace rgc {
         const std::size_t per = (((b + n - 1) / n) + 4095) & ~std::size_t(4095);
         const std::size_t off = (std::size_t)id * per;
         if (off < b) {
-          std::memcpy(d + off, s + off, std::min(per, b - off));
+          stage_copy(d + off, s + off, std::min(per, b - off));
         }
         lk.lock();
         if (--pending_ == 0) {
@@ -177,12 +209,15 @@ namespace rgc {
 
   static CopyPool* copy_pool() {
     if (!g_copy_pool) {
-      int n = 8;
+      // one thread moves 4-10 GB/s; the default shares the hardware threads between the
+      // ranks of this node (torchrun's LOCAL_WORLD_SIZE), at most 32 per rank
+      const int hw    = std::max(1, (int)std::thread::hardware_concurrency());
+      const char* lws = std::getenv("LOCAL_WORLD_SIZE");
+      int n = std::min(32, std::max(2, hw / std::max(1, lws ? std::atoi(lws) : 1)));
       if (const char* s = std::getenv("RGC_COPY_THREADS")) {
         n = std::atoi(s);
       }
-      const int hw = (int)std::thread::hardware_concurrency();
-      n = std::max(1, std::min(n, std::max(1, hw / 2)));
+      n = std::max(1, std::min(n, 64));
       g_copy_pool = new CopyPool(n);
     }
     return g_copy_pool;
@@ -683,8 +718,24 @@ extern "C" {
     for (auto& e : c.ev) {
       RGC_CUDA(cudaEventCreate(&e));
     }
+    {
+      cudaMemPool_t pool = nullptr;
+      RGC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+      std::uint64_t keep = ~std::uint64_t(0); // freed columns stay cached for the next container
+      RGC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     c.launches    = 0;
     c.initialized = true;
+    return RGC_OK;
+  }
+
+  int rgc_trim_memory(void) {
+    RGC_REQUIRE_INIT();
+    auto& c = ctx();
+    RGC_CUDA(cudaStreamSynchronize(c.stream));
+    cudaMemPool_t pool = nullptr;
+    RGC_CUDA(cudaDeviceGetDefaultMemPool(&pool, c.device));
+    RGC_CUDA(cudaMemPoolTrimTo(pool, 0));
     return RGC_OK;
   }
 
@@ -695,6 +746,12 @@ extern "C" {
     }
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
+    {
+      cudaMemPool_t pool = nullptr;
+      if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) {
+        cudaMemPoolTrimTo(pool, 0);
+      }
+    }
     rgc_comm_destroy();
     io_release_lanes();
     pair_release_plans();
@@ -956,11 +1013,16 @@ extern "C" {
     return RGC_OK;
   }
 
+  // Particle columns come from the device's stream-ordered memory pool (release threshold
+  // unlimited, set in rgc_init): a container that is dropped and re-created — what a script
+  // does per species and step — gets its memory back without a device-wide cudaFree /
+  // cudaMalloc round trip (tens of ms for GB-sized columns).  rgc_trim_memory() returns the
+  // cached blocks to the device.
   static void free_columns(rgc_particles_t* p) {
     for (auto& q : p->col) {
       for (auto& c : q) {
         if (c) {
-          cudaFree(c);
+          cudaFreeAsync(c, ctx().stream);
           c = nullptr;
         }
       }
@@ -971,8 +1033,7 @@ extern "C" {
     if (p) {
       if (ctx().initialized) {
         cudaStreamSynchronize(ctx().copy_stream);
-        cudaStreamSynchronize(ctx().stream);
-        free_columns(p);
+        free_columns(p); // ordered behind everything already enqueued on the compute stream
       }
       delete p;
     }
@@ -985,11 +1046,11 @@ extern "C" {
   }
 
   static int alloc_column(float** col, std::size_t pitch) {
-    cudaError_t err = cudaMalloc(col, pitch * sizeof(float));
+    cudaError_t err = cudaMallocAsync(reinterpret_cast<void**>(col), pitch * sizeof(float), ctx().stream);
     if (err != cudaSuccess) {
       cudaGetLastError();
       *col = nullptr;
-      return fail(RGC_ERR_OOM, "cudaMalloc of a %zu-particle column failed: %s", pitch,
+      return fail(RGC_ERR_OOM, "cudaMallocAsync of a %zu-particle column failed: %s", pitch,
                   cudaGetErrorString(err));
     }
     RGC_CUDA(cudaMemsetAsync(*col, 0, pitch * sizeof(float), ctx().stream));
@@ -1057,8 +1118,7 @@ extern "C" {
           RGC_TRY(alloc_column(&bigger, new_pitch));
           RGC_CUDA(cudaMemcpyAsync(bigger, c, p->nalloc * sizeof(float),
                                    cudaMemcpyDeviceToDevice, ctx().stream));
-          RGC_CUDA(cudaStreamSynchronize(ctx().stream));
-          RGC_CUDA(cudaFree(c));
+          RGC_CUDA(cudaFreeAsync(c, ctx().stream));
           c = bigger;
         }
       }

@@ -207,8 +207,8 @@ namespace rgc {
       xmax = std::max(xmax, tab_x[k]);
     }
     const int nbx = (int)((nbins + kLitThreads - 1) / kLitThreads);
-    // slices of sources: ~4 CTAs per SM over the whole grid, at least 8 sources each
-    const std::size_t want_slices = (std::size_t)std::max(1, 4 * c.sm_count / nbx);
+    // slices of sources: ~8 CTAs per SM over the whole grid, at least 8 sources each
+    const std::size_t want_slices = (std::size_t)std::max(1, 8 * c.sm_count / nbx);
     const std::size_t per_slice   = std::max<std::size_t>(8, (n + want_slices - 1) / want_slices);
     const int         nslices     = (int)std::max<std::size_t>(1, (n + per_slice - 1) / per_slice);
     // one packed upload: [bins | tab_x | tab_y | e_peak, w1, w2 of the sources]

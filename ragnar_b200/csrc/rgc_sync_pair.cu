@@ -941,10 +941,14 @@ namespace rgc {
   }
 
   // msum[b] = S0 of bucket b, msum[nb + b] = S1: fp64 sums over the bucket's pieces,
-  // lane-strided then a fixed shuffle tree
+  // lane-strided then a fixed shuffle tree.  Also counts (roofline accounting, integer
+  // atomics) the pairs of the bucket whose cell pair is not identically zero: what an
+  // ideal kernel would have to evaluate.
   __global__ void __launch_bounds__(kPThreads)
     pair_moments_kernel(const int* __restrict__ tot, int nb, const float2* __restrict__ piece_mom,
-                        double* __restrict__ msum) {
+                        double* __restrict__ msum, const int2* __restrict__ slot_i,
+                        const int* __restrict__ bin_of_slot, const float4* __restrict__ coef_dh,
+                        int nslots, unsigned long long* __restrict__ ontable) {
     __shared__ int bstart[kPMaxBuckets + 2], pstart[kPMaxBuckets + 2], tmp[2 * kPWarps];
     block_scan_buckets(tot, nb, bstart, pstart, tmp);
     const int lane = threadIdx.x & 31;
@@ -958,14 +962,22 @@ namespace rgc {
       s0 += (double)m.x;
       s1 += (double)m.y;
     }
+    int live = 0;
+    for (int sl = lane; sl < nslots; sl += 32) {
+      live += (bin_of_slot[sl] >= 0 && coef_dh[max(slot_i[sl].x + b, 0)].x != 0.0f) ? 1 : 0;
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       s0 += __shfl_xor_sync(0xffffffffu, s0, off);
       s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+      live += __shfl_xor_sync(0xffffffffu, live, off);
     }
     if (lane == 0) {
       msum[b]      = s0;
       msum[nb + b] = s1;
+      if (tot[b] != 0 && live != 0) {
+        atomicAdd(ontable, (unsigned long long)tot[b] * (unsigned long long)live);
+      }
     }
   }
 
@@ -1173,6 +1185,7 @@ namespace rgc {
       }
     }
     plan_cache().clear();
+
   }
 
   static int cached_pair_plan(const TablePlan& tp, const float* bins_e_syn,
@@ -1353,7 +1366,7 @@ namespace rgc {
       const char* ns  = std::getenv("RGC_PAIR_NO_SKIP"); // test knob
       P.force_groups  = (ns && ns[0] == '1') ? ((1u << pp.gpw) - 1u) : 0u;
     }
-    P.lane_evals = reinterpret_cast<unsigned long long*>(d_poison) + 1; // next 8 bytes of the result buffer
+    P.lane_evals = reinterpret_cast<unsigned long long*>(d_poison) + 1; // [issued, on-table] behind the flag
     P.sorted    = reinterpret_cast<float2*>(sb + off_sort);
     P.piece_mom = reinterpret_cast<float2*>(sb + off_mom);
     P.partials  = reinterpret_cast<double*>(sb + off_part);
@@ -1404,7 +1417,8 @@ namespace rgc {
       RGC_CUDA(cudaGetLastError());
       RGC_CUDA(cudaEventRecord(c.ev[4], c.stream));
       pair_moments_kernel<<<(pp.nb + kPWarps - 1) / kPWarps, kPThreads, 0, c.stream>>>(
-        P.tot, pp.nb, P.piece_mom, d_msum);
+        P.tot, pp.nb, P.piece_mom, d_msum, P.slot_i, reinterpret_cast<const int*>(cp->dev + cp->off_map),
+        P.coef_dh, pp.nslots, P.lane_evals + 1);
       RGC_CUDA(cudaGetLastError());
       pair_final_kernel<<<(pp.nslots + kPWarps - 1) / kPWarps, kPThreads, 0, c.stream>>>(
         P.partials, pair_ctas, pp.nslots, P.slot_i, P.slot_f,

@@ -508,14 +508,14 @@ namespace rgc {
     }
     // per-bin sums are accumulated on the device (one small buffer that survives the
     // scratch re-layouts of the launches), all-reduced once and read back once:
-    // [nbins doubles | poison flag, issued evaluations | nbins floats: e_syn]
+    // [nbins doubles | poison flag, issued evaluations, on-table pairs | nbins floats: e_syn]
     void* result = nullptr;
-    RGC_TRY(ensure_result(nbins * sizeof(double) + 16 + nbins * sizeof(float), &result));
+    RGC_TRY(ensure_result(nbins * sizeof(double) + 24 + nbins * sizeof(float), &result));
     double* d_acc    = static_cast<double*>(result);
     int*    d_poison = reinterpret_cast<int*>(d_acc + nbins);
-    float*  d_bins   = reinterpret_cast<float*>(d_acc + nbins + 2);
+    float*  d_bins   = reinterpret_cast<float*>(d_acc + nbins + 3);
     RGC_CUDA(cudaEventRecord(c.ev[0], c.stream));
-    RGC_CUDA(cudaMemsetAsync(d_acc, 0, nbins * sizeof(double) + 16, c.stream));
+    RGC_CUDA(cudaMemsetAsync(d_acc, 0, nbins * sizeof(double) + 24, c.stream));
     float main_ms  = 0.f;
     bool  deferred = false;
     // ---- small populations: the reference's own float arithmetic per pair
@@ -643,8 +643,8 @@ namespace rgc {
       RGC_TRY(allreduce_sum_f64(d_acc, nbins));
     }
     // one D2H: [per-bin sums | poison flag | issued hinge evaluations]
-    std::vector<double> back(nbins + 2);
-    RGC_CUDA(cudaMemcpyAsync(back.data(), d_acc, (nbins + 2) * sizeof(double),
+    std::vector<double> back(nbins + 3);
+    RGC_CUDA(cudaMemcpyAsync(back.data(), d_acc, (nbins + 3) * sizeof(double),
                              cudaMemcpyDeviceToHost, c.stream));
     RGC_CUDA(cudaEventRecord(c.ev[1], c.stream));
     RGC_CUDA(cudaStreamSynchronize(c.stream));
@@ -656,6 +656,8 @@ namespace rgc {
       unsigned long long le = 0;
       std::memcpy(&le, &back[nbins + 1], sizeof(le));
       c.last_lane_evals = (double)le;
+      std::memcpy(&le, &back[nbins + 2], sizeof(le));
+      c.last_ontable_evals = (double)le;
     }
     if (deferred && pair_single_pass(src.n)) {
       RGC_TRY(collect_pair_times(&main_ms));
@@ -722,6 +724,14 @@ extern "C" {
   int rgc_last_pair_lane_evals(double* lane_evals) {
     if (lane_evals) {
       *lane_evals = ctx().last_lane_evals;
+    }
+    return RGC_OK;
+  }
+
+  int rgc_last_pair_ontable_evals(double* evals) {
+    RGC_REQUIRE_INIT();
+    if (evals) {
+      *evals = ctx().last_ontable_evals;
     }
     return RGC_OK;
   }

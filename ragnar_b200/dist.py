@@ -64,3 +64,38 @@ def allreduce_sum_host(dist, array: np.ndarray) -> np.ndarray:
             t = t.cuda()
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.cpu().numpy()
+
+
+def bind_to_gpu_numa(device_index: int) -> dict:
+    """Pin this process (and the threads it creates afterwards: the library's staging pool)
+    to the CPUs of the NUMA node the GPU hangs off, so pinned host buffers allocated from
+    now on are node-local (first touch) and H2D copies do not cross the socket link.
+    Returns what was done; a box without NUMA information is left alone."""
+    import os
+
+    info = {"bound": False}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]  # 0000:1b:00.0
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, cpus=len(cpus))
+    except Exception as e:  # no NVML / sysfs: nothing to bind to
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info

@@ -59,8 +59,11 @@ if rank == 0:
     nz = want_h64 > 0
     herr = float(np.max(np.abs(h64[nz] - want_h64[nz]) / want_h64[nz]))
     add = float(np.max(np.abs(spec[big] - solo_spec[big]) / solo_spec[big]))
+    # shards of <= 2^19 particles take the literal path while the one-rank run of the whole
+    # population takes the hinge pipeline: then the two differ like the pipeline and the oracle
+    same_path = (cnt <= (1 << 19)) == (n <= (1 << 19))
     ok = (err < 1e-5 and herr < 1e-5 and np.array_equal(counts, want_c)
-          and np.array_equal(counts, solo_hist[1]) and add < 1e-6
+          and np.array_equal(counts, solo_hist[1]) and add < (1e-6 if same_path else 1e-5)
           and np.array_equal(spec == 0, want == 0) and np.all(np.isfinite(spec0)))
     print(f"[dist_check] world={world} exchange: {cabi.comm_exchange_kind()}", flush=True)
     print(f"[dist_check] world={world} n={n}: spectrum rel err vs oracle {err:.2e}, "
