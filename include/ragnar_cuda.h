@@ -176,6 +176,22 @@ int rgc_particles_generate(rgc_particles_t* p, int kind, uint64_t seed,
  * reference's exact float/double promotions) */
 int rgc_linspace(float start, float stop, size_t num, float* out);
 int rgc_logspace(float start, float stop, size_t num, float* out);
+/* The same grids built ON THE DEVICE into a new buffer (grids of >= 1e6 points),
+ * bit-identical to rgc_linspace / rgc_logspace: Linspace is IEEE float arithmetic; Logspace
+ * evaluates pow(10, exponent) on the device and re-evaluates on the host, with the reference's
+ * libm, the few elements (~1e-8 of them) whose double result lies within 16 ulp of a float
+ * rounding boundary.  Same errors as the host versions. */
+int rgc_linspace_device(float start, float stop, size_t num, rgc_buf_t** out);
+int rgc_logspace_device(float start, float stop, size_t num, rgc_buf_t** out);
+/* TabulatedFunction<LG>::findMinMax — src/containers/tabulation.cpp:84-102 (Kokkos MinMax
+ * reduce: `<` / `>` comparisons, NaNs never win) on a device-resident float buffer */
+int rgc_buf_minmax(const rgc_buf_t* buf, float* min_out, float* max_out);
+/* InterpolateTabulatedFunction<LG> — src/containers/tabulation.hpp:19-53 — of a device-resident
+ * table (tab_x, tab_y) at every element of x0, the reference's float sequence bit for bit
+ * (glibc's log10f restated on the device); verify() errors of tabulation.cpp:104-117 are
+ * returned as RGC_ERR_INVALID.  *out is a new float buffer of x0's length. */
+int rgc_tabulated_eval(int loggrid, const rgc_buf_t* tab_x, const rgc_buf_t* tab_y, float yfill,
+                       const rgc_buf_t* x0, rgc_buf_t** out);
 /* sync::Ffunc_integrand — src/physics/synchrotron.cpp:28-46 */
 int rgc_sync_ffunc_integrand(float x, float* out);
 /* sync::TabulateFfunc — src/physics/synchrotron.cpp:48-65 (cached per (n,xmin,xmax)) */
@@ -224,6 +240,19 @@ int rgc_sync_spectrum_dist(const float* gbeta, const float* f, size_t ndist,
                            int islog_bins_prtls, const float* bins_e_syn, size_t nbins,
                            const float* tab_x, const float* tab_y, size_t tab_n, float g_syn,
                            float e_syn_at_g_syn, float* out_spec, double* out_spec64);
+/* A batch of distributions on the SAME bins (steps x species of a run: the caller of the path,
+ * legacy/simulation.cpp.bak:67-219): f holds nbatch rows of ndist values, out_spec /
+ * out_spec64 nbatch rows of nbins.  mode 0: every (distribution, bin, photon bin) term with
+ * the reference's float arithmetic, as rgc_sync_spectrum_dist; mode 1: the kernel matrix
+ * K[g][j] = e_syn[j] * gbeta[g] * F(e_syn[j] / e_peak[g]) is built once and the batch is
+ * contracted in fp64, out = f . K (each term within three float roundings, ~1e-7, of the
+ * reference's); mode -1: the contraction from 64 distributions on (where it is the faster
+ * one, profiles/r2_fromdist_batch.txt). */
+int rgc_sync_spectrum_dist_batch(const float* gbeta, const float* f, size_t nbatch, size_t ndist,
+                                 int islog_bins_prtls, const float* bins_e_syn, size_t nbins,
+                                 const float* tab_x, const float* tab_y, size_t tab_n,
+                                 float g_syn, float e_syn_at_g_syn, int mode, float* out_spec,
+                                 double* out_spec64);
 
 /* ICSpectrum + ic::Kernel + ic::KNfunc — src/physics/ic.cpp:15-46,
  * src/physics/ic.hpp:20-85.  (g_prtls, f_prtls): particle TabulatedDistribution;

@@ -63,6 +63,10 @@ SIGNATURES = {
                                          C.c_float, C.c_float]),
     "rgc_linspace": (C.c_int, [C.c_float, C.c_float, _sz, _f32p]),
     "rgc_logspace": (C.c_int, [C.c_float, C.c_float, _sz, _f32p]),
+    "rgc_linspace_device": (C.c_int, [C.c_float, C.c_float, _sz, _vpp]),
+    "rgc_logspace_device": (C.c_int, [C.c_float, C.c_float, _sz, _vpp]),
+    "rgc_buf_minmax": (C.c_int, [_vp, _f32p, _f32p]),
+    "rgc_tabulated_eval": (C.c_int, [C.c_int, _vp, _vp, C.c_float, _vp, _vpp]),
     "rgc_sync_ffunc_integrand": (C.c_int, [C.c_float, _f32p]),
     "rgc_sync_tabulate_ffunc": (C.c_int, [_sz, C.c_float, C.c_float, _f32p, _f32p]),
     "rgc_interpolate": (C.c_int, [C.c_int, C.c_float, _f32p, _f32p, _sz, C.c_float, _f32p]),
@@ -73,6 +77,8 @@ SIGNATURES = {
                                               C.c_float, C.c_float, C.c_float, _f32p, _f64p]),
     "rgc_sync_spectrum_dist": (C.c_int, [_f32p, _f32p, _sz, C.c_int, _f32p, _sz, _f32p, _f32p,
                                          _sz, C.c_float, C.c_float, _f32p, _f64p]),
+    "rgc_sync_spectrum_dist_batch": (C.c_int, [_f32p, _f32p, _sz, _sz, C.c_int, _f32p, _sz, _f32p, _f32p,
+                                               _sz, C.c_float, C.c_float, C.c_int, _f32p, _f64p]),
     "rgc_ic_spectrum": (C.c_int, [_f32p, _f32p, _sz, C.c_int, _f32p, _f32p, _sz, _f32p, _sz,
                                   _f32p, _f64p]),
     "rgc_last_kernel_ms": (C.c_int, [_f32p]),
@@ -342,6 +348,65 @@ def linspace(start, stop, num) -> np.ndarray:
     return out
 
 
+class DeviceArray:
+    """Owner of an rgc_buf_t handle (a device-resident 1-D float array)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def from_host(cls, a) -> "DeviceArray":
+        a = _f32(a)
+        h = _vp()
+        check(lib().rgc_buf_from_host(1, a.ctypes.data_as(_vp), a.size, C.byref(h)))
+        return cls(h)
+
+    def __len__(self) -> int:
+        return int(lib().rgc_buf_size(self.h))
+
+    def to_host(self) -> np.ndarray:
+        out = np.empty(len(self), np.float32)
+        if len(self):
+            check(lib().rgc_buf_to_host(self.h, 0, len(self), out.ctypes.data_as(_vp)))
+        return out
+
+    def minmax(self):
+        mn, mx = C.c_float(), C.c_float()
+        check(lib().rgc_buf_minmax(self.h, C.byref(mn), C.byref(mx)))
+        return mn.value, mx.value
+
+    def release(self):
+        if self.h is not None and self.h.value:
+            lib().rgc_buf_release(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def linspace_device(start, stop, num) -> DeviceArray:
+    h = _vp()
+    check(lib().rgc_linspace_device(start, stop, num, C.byref(h)))
+    return DeviceArray(h)
+
+
+def logspace_device(start, stop, num) -> DeviceArray:
+    h = _vp()
+    check(lib().rgc_logspace_device(start, stop, num, C.byref(h)))
+    return DeviceArray(h)
+
+
+def tabulated_eval(loggrid: bool, tab_x: DeviceArray, tab_y: DeviceArray, x0: DeviceArray,
+                   yfill: float = 0.0) -> DeviceArray:
+    """InterpolateTabulatedFunction<LG> of a device-resident table at every element of x0"""
+    h = _vp()
+    check(lib().rgc_tabulated_eval(int(loggrid), tab_x.h, tab_y.h, yfill, x0.h, C.byref(h)))
+    return DeviceArray(h)
+
+
 def ffunc_integrand(x: float) -> float:
     out = C.c_float()
     check(lib().rgc_sync_ffunc_integrand(x, C.byref(out)))
@@ -407,6 +472,23 @@ def sync_spectrum_dist(gbeta, f, islog, bins_e_syn, g_syn, e_at, table=None):
     check(lib().rgc_sync_spectrum_dist(_ptr(gbeta), _ptr(f), len(gbeta), int(islog), _ptr(bins),
                                        len(bins), _ptr(tx), _ptr(ty), len(tx), g_syn, e_at,
                                        _ptr(s32), _ptr(s64, _f64p)))
+    return s32, s64
+
+
+def sync_spectrum_dist_batch(gbeta, f_batch, islog, bins_e_syn, g_syn, e_at, table=None, mode=-1):
+    """f_batch: [nbatch, len(gbeta)] distributions on shared bins -> (spec f32, spec f64), each
+    [nbatch, len(bins)].  mode 0 literal terms, 1 kernel-matrix contraction, -1 automatic."""
+    gbeta, bins = _f32(gbeta), _f32(bins_e_syn)
+    fb = np.ascontiguousarray(f_batch, dtype=np.float32)
+    if fb.ndim != 2 or fb.shape[1] != len(gbeta):
+        raise ValueError("f_batch must be [nbatch, len(gbeta)]")
+    tx, ty = table if table is not None else tabulate_ffunc()
+    tx, ty = _f32(tx), _f32(ty)
+    s32 = np.zeros((fb.shape[0], len(bins)), np.float32)
+    s64 = np.zeros((fb.shape[0], len(bins)), np.float64)
+    check(lib().rgc_sync_spectrum_dist_batch(_ptr(gbeta), _ptr(fb), fb.shape[0], len(gbeta), int(islog),
+                                             _ptr(bins), len(bins), _ptr(tx), _ptr(ty), len(tx), g_syn,
+                                             e_at, mode, _ptr(s32), _ptr(s64, _f64p)))
     return s32, s64
 
 

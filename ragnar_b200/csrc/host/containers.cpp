@@ -142,13 +142,28 @@ namespace rgb {
   template class Array1D<double>;
 
   // ------------------------------------------------------------------- spaces
+  // Grids beyond kDeviceGridMin points are built on the device (bit-identical, see
+  // rgc_spaces.cu) and never staged through a host vector; smaller ones — bin edges, F
+  // tables — keep their host mirror, which the kernels' host-side planning reads.
+  constexpr std::size_t kDeviceGridMin = std::size_t(1) << 16;
+
   Array1D<real_t> Linspace(real_t start, real_t stop, std::size_t num) {
+    if (num > kDeviceGridMin) {
+      rgc_buf_t* buf = nullptr;
+      check(rgc_linspace_device(start, stop, num, &buf));
+      return Array1D<real_t>::adopt(buf);
+    }
     std::vector<real_t> edges(num);
     check(rgc_linspace(start, stop, num, edges.data()));
     return Array1D<real_t> { edges };
   }
 
   Array1D<real_t> Logspace(real_t start, real_t stop, std::size_t num) {
+    if (num > kDeviceGridMin) {
+      rgc_buf_t* buf = nullptr;
+      check(rgc_logspace_device(start, stop, num, &buf));
+      return Array1D<real_t>::adopt(buf);
+    }
     std::vector<real_t> edges(num);
     check(rgc_logspace(start, stop, num, edges.data()));
     return Array1D<real_t> { edges };
@@ -172,10 +187,14 @@ namespace rgb {
     // reference tabulation.cpp:84-117
     m_xmin = std::numeric_limits<real_t>::max();
     m_xmax = std::numeric_limits<real_t>::lowest();
-    const real_t* x = m_x.host_data();
-    for (std::size_t i = 0; i < m_n; ++i) {
-      m_xmin = x[i] < m_xmin ? x[i] : m_xmin;
-      m_xmax = x[i] > m_xmax ? x[i] : m_xmax;
+    if (m_n > kDeviceGridMin) { // large tables: the MinMax reduction runs where the data is
+      check(rgc_buf_minmax(m_x.handle(), &m_xmin, &m_xmax));
+    } else {
+      const real_t* x = m_x.host_data();
+      for (std::size_t i = 0; i < m_n; ++i) {
+        m_xmin = x[i] < m_xmin ? x[i] : m_xmin;
+        m_xmax = x[i] > m_xmax ? x[i] : m_xmax;
+      }
     }
     if (m_y.extent(0) != m_n) {
       throw std::range_error("y.size != x.size in TabulatedFunction");

@@ -154,11 +154,14 @@ namespace rgc {
   int  launch_scatter_add(const double* src, const int* binmap, int nslots, double* d_acc);
   // literal evaluation (rgc_sync_literal.cu): the reference's float term per pair, summed
   // in fp64; sources = the first n particles of `prtls`, or n host triples when src_ep != 0
+  // (then src_w1 holds nbatch rows of n weights and d_out nbatch rows of nbins sums;
+  // contract = true builds the kernel matrix once and contracts the batch in fp64)
   std::size_t literal_max_n(); // RGC_LITERAL_MAX_N, default 2^19
   int  run_spectrum_literal(const rgc_particles* prtls, std::size_t n, float B0, float g_syn,
                             float e_at, const float* src_ep, const float* src_w1,
                             const float* src_w2, const float* bins_e_syn, std::size_t nbins,
-                            const float* tab_x, const float* tab_y, std::size_t T, double* d_out);
+                            const float* tab_x, const float* tab_y, std::size_t T, double* d_out,
+                            std::size_t nbatch = 1, bool contract = false);
 } // namespace rgc
 
 // ------------------------------------------------------------ opaque handles

@@ -130,7 +130,12 @@ namespace rgc {
   }
 
   static void stage_copy(char* dst, const char* src, std::size_t bytes) {
-    static const bool avx2 = __builtin_cpu_supports("avx2");
+    // RGC_STAGE_NT=0 falls back to memcpy (measured on the bench box, tools/bench_fromarrays.py:
+    // 77-78 ms against 79-83 ms for the nine columns of 1e8 particles)
+    static const bool avx2 = __builtin_cpu_supports("avx2") && [] {
+      const char* e = std::getenv("RGC_STAGE_NT");
+      return !(e && e[0] == '0');
+    }();
     if (avx2 && (reinterpret_cast<std::uintptr_t>(dst) & 31u) == 0 && bytes >= 4096) {
       stream_copy_avx2(dst, src, bytes);
     } else {

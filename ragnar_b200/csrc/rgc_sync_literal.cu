@@ -46,9 +46,10 @@ namespace rgc {
     const float* e[3];
     const float* b[3];
     const float* src_ep; // e_peak of every source
-    const float* src_w1; // term = ((w1 * e_syn) [* w2]) * F
+    const float* src_w1; // term = ((w1 * e_syn) [* w2]) * F; [nbatch][nsrc]: one row per batch item
     const float* src_w2; // nullptr: no second factor
     std::size_t  nsrc;
+    int          nbatch; // blockIdx.z: distributions sharing (e_peak, w2) and the photon bins
     std::size_t  src_per_slice;
     float        B0, g_syn, e_at;
     const float* bins;
@@ -58,7 +59,7 @@ namespace rgc {
     const float* tab_den; // [T - 1] log10f(x[k + 1] / x[k])
     int          T;
     float        xmin, xmax, Lspan; // Lspan = log10f(xmax / xmin)
-    double*      partials;          // [slices][nbins]
+    double*      partials;          // [nbatch][slices][nbins]
   };
 
   __device__ const LogfEntry g_logf_tab[16] = RGC_LOGF_TAB_INIT;
@@ -135,7 +136,7 @@ namespace rgc {
         if (i < s1) {
           if (P.src_ep) {
             ep = P.src_ep[i];
-            w1 = P.src_w1[i];
+            w1 = P.src_w1[(std::size_t)blockIdx.z * P.nsrc + i];
             w2 = has_w2 ? P.src_w2[i] : 1.0f;
           } else {
             literal_prologue(P, i, ep, w1);
@@ -162,22 +163,104 @@ namespace rgc {
       }
     }
     if (j < P.nbins) {
-      P.partials[(std::size_t)blockIdx.y * P.nbins + j] = acc;
+      P.partials[((std::size_t)blockIdx.z * gridDim.y + blockIdx.y) * P.nbins + j] = acc;
     }
   }
 
-  // out[j] = sum over slices, in slice order
+  // out[b][j] = sum over slices, in slice order (b = blockIdx.y)
   __global__ void literal_reduce_kernel(const double* __restrict__ partials, int nslices, int nbins,
                                         double* __restrict__ out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nbins) {
       return;
     }
-    double s = 0.0;
+    const double* part = partials + (std::size_t)blockIdx.y * nslices * nbins;
+    double        s    = 0.0;
     for (int c = 0; c < nslices; ++c) {
-      s += partials[(std::size_t)c * nbins + j];
+      s += part[(std::size_t)c * nbins + j];
     }
-    out[j] = s;
+    out[(std::size_t)blockIdx.y * nbins + j] = s;
+  }
+
+  // ---- the contraction form of a batch of distributions:
+  //   out[b][j] = sum_g f[b][g] * K[g][j],   K[g][j] = e_syn[j] * w2[g] * F(e_syn[j] / e_peak[g])
+  // K is built once per (distribution bins, photon bins) by the literal machinery (F is the
+  // reference's float value), the products are formed in double: every term equals the
+  // reference's float term ((f * e_syn) * w2) * F up to its three float roundings (~1e-7).
+  __global__ void __launch_bounds__(kLitThreads)
+    kernel_matrix_kernel(const __grid_constant__ LiteralParams P, double* __restrict__ K) {
+    __shared__ LogfEntry lt[16];
+    if (threadIdx.x < 16) {
+      lt[threadIdx.x] = g_logf_tab[threadIdx.x];
+    }
+    __syncthreads();
+    const int j = blockIdx.x * kLitThreads + threadIdx.x;
+    const int g = blockIdx.y;
+    if (j >= P.nbins) {
+      return;
+    }
+    const float e_syn = P.bins[j];
+    const float ep    = P.src_ep[g];
+    double      k     = 0.0;
+    if (ep > 0.0f) {
+      const float F = literal_interp(P, lt, e_syn / ep);
+      k = (double)e_syn * (P.src_w2 ? (double)P.src_w2[g] : 1.0) * (double)F;
+    }
+    K[(std::size_t)g * P.nbins + j] = k;
+  }
+
+  // C[b][j] = sum_g A[b][g] K[g][j] in fp64, g ascending (a fixed order): 64 x 64 output tile
+  // per CTA, 4 x 4 per thread, K and A staged through shared memory 16 rows at a time.
+  // Rows of A whose e_peak fails `e_peak > 0` are skipped like the reference skips them.
+  constexpr int kCtTile = 64, kCtK = 16;
+  __global__ void __launch_bounds__(256)
+    dist_contract_kernel(const float* __restrict__ A, const float* __restrict__ ep,
+                         const double* __restrict__ K, int nbatch, int G, int M,
+                         double* __restrict__ C) {
+    __shared__ double sA[kCtK][kCtTile + 1];
+    __shared__ double sK[kCtK][kCtTile];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int b0 = blockIdx.y * kCtTile, j0 = blockIdx.x * kCtTile;
+    double    acc[4][4] = {};
+    for (int g0 = 0; g0 < G; g0 += kCtK) {
+      for (int i = threadIdx.x; i < kCtK * kCtTile; i += 256) {
+        const int gg = i / kCtTile, c = i % kCtTile;
+        const int g  = g0 + gg;
+        // A transposed into [g][b]; a skipped source contributes nothing whatever f holds
+        const bool live = g < G && b0 + c < nbatch && ep[g] > 0.0f;
+        sA[gg][c] = live ? (double)A[(std::size_t)(b0 + c) * G + g] : 0.0;
+        sK[gg][c] = (g < G && j0 + c < M) ? K[(std::size_t)g * M + j0 + c] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int gg = 0; gg < kCtK; ++gg) {
+        double a[4], k[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          a[r] = sA[gg][ty * 4 + r];
+          k[r] = sK[gg][tx * 4 + r];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[r][q] = fma(a[r], k[q], acc[r][q]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int b = b0 + ty * 4 + r;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + tx * 4 + q;
+        if (b < nbatch && j < M) {
+          C[(std::size_t)b * M + j] = acc[r][q];
+        }
+      }
+    }
   }
 
   // read on every call: tests switch paths with the environment variable
@@ -195,10 +278,14 @@ namespace rgc {
   int run_spectrum_literal(const rgc_particles* prtls, std::size_t n, float B0, float g_syn,
                            float e_at, const float* src_ep, const float* src_w1,
                            const float* src_w2, const float* bins_e_syn, std::size_t nbins,
-                           const float* tab_x, const float* tab_y, std::size_t T, double* d_out) {
+                           const float* tab_x, const float* tab_y, std::size_t T, double* d_out,
+                           std::size_t nbatch, bool contract) {
     auto& c = ctx();
-    if (nbins == 0) {
+    if (nbins == 0 || nbatch == 0) {
       return RGC_OK;
+    }
+    if (nbatch > 65535) {
+      return fail(RGC_ERR_INVALID, "at most 65535 distributions per batch (got %zu)", nbatch);
     }
     // the reference's findMinMax over the x array (tabulation.cpp:84-102)
     float xmin = tab_x[0], xmax = tab_x[0];
@@ -208,28 +295,31 @@ namespace rgc {
     }
     const int nbx = (int)((nbins + kLitThreads - 1) / kLitThreads);
     // slices of sources: ~8 CTAs per SM over the whole grid, at least 8 sources each
-    const std::size_t want_slices = (std::size_t)std::max(1, 8 * c.sm_count / nbx);
+    const std::size_t want_slices =
+      (std::size_t)std::max<std::size_t>(1, 8 * (std::size_t)c.sm_count / ((std::size_t)nbx * nbatch));
     const std::size_t per_slice   = std::max<std::size_t>(8, (n + want_slices - 1) / want_slices);
     const int         nslices     = (int)std::max<std::size_t>(1, (n + per_slice - 1) / per_slice);
     // one packed upload: [bins | tab_x | tab_y | e_peak, w1, w2 of the sources]
     const std::size_t nsrc_f = src_ep ? n : 0;
-    std::vector<float> pack(nbins + 2 * T + 3 * nsrc_f);
+    std::vector<float> pack(nbins + 2 * T + (2 + nbatch) * nsrc_f);
     std::copy(bins_e_syn, bins_e_syn + nbins, pack.begin());
     std::copy(tab_x, tab_x + T, pack.begin() + nbins);
     std::copy(tab_y, tab_y + T, pack.begin() + nbins + T);
     if (src_ep) {
-      float* ps = pack.data() + nbins + 2 * T;
+      float* ps = pack.data() + nbins + 2 * T; // [e_peak | w2 | w1 rows]
       std::copy(src_ep, src_ep + n, ps);
-      std::copy(src_w1, src_w1 + n, ps + n);
       if (src_w2) {
-        std::copy(src_w2, src_w2 + n, ps + 2 * n);
+        std::copy(src_w2, src_w2 + n, ps + n);
       }
+      std::copy(src_w1, src_w1 + nbatch * n, ps + 2 * n);
     }
     auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
     const std::size_t o_pack = 0;
     const std::size_t o_den  = align(o_pack + pack.size() * sizeof(float));
     const std::size_t o_part = align(o_den + T * sizeof(float));
-    const std::size_t total  = o_part + (std::size_t)nslices * nbins * sizeof(double);
+    const std::size_t part_bytes =
+      contract ? n * nbins * sizeof(double) : nbatch * (std::size_t)nslices * nbins * sizeof(double);
+    const std::size_t total = o_part + part_bytes;
     void* scratch = nullptr;
     RGC_TRY(ensure_scratch(total, &scratch));
     char*  sb     = static_cast<char*>(scratch);
@@ -239,8 +329,8 @@ namespace rgc {
     if (src_ep) {
       const float* d_src = d_pack + nbins + 2 * T;
       P.src_ep = d_src;
-      P.src_w1 = d_src + n;
-      P.src_w2 = src_w2 ? d_src + 2 * n : nullptr;
+      P.src_w2 = src_w2 ? d_src + n : nullptr;
+      P.src_w1 = d_src + 2 * n;
     } else {
       for (int d = 0; d < 3; ++d) {
         P.u[d] = prtls->col[RGC_Q_U][d];
@@ -249,6 +339,7 @@ namespace rgc {
       }
     }
     P.nsrc          = n;
+    P.nbatch        = (int)nbatch;
     P.src_per_slice = per_slice;
     P.B0            = B0;
     P.g_syn         = g_syn;
@@ -268,10 +359,23 @@ namespace rgc {
       P.tab_x, P.T, reinterpret_cast<float*>(sb + o_den));
     RGC_CUDA(cudaGetLastError());
     RGC_CUDA(cudaEventRecord(c.ev[2], c.stream));
-    sync_literal_kernel<<<dim3((unsigned)nbx, (unsigned)nslices), kLitThreads, 0, c.stream>>>(P);
+    if (contract) {
+      // K[g][j] once, then the fp64 contraction over the batch
+      kernel_matrix_kernel<<<dim3((unsigned)nbx, (unsigned)n), kLitThreads, 0, c.stream>>>(P, P.partials);
+      RGC_CUDA(cudaGetLastError());
+      dist_contract_kernel<<<dim3((unsigned)((nbins + kCtTile - 1) / kCtTile),
+                                  (unsigned)((nbatch + kCtTile - 1) / kCtTile)),
+                             256, 0, c.stream>>>(P.src_w1, P.src_ep, P.partials, (int)nbatch, (int)n,
+                                                 (int)nbins, d_out);
+      RGC_CUDA(cudaGetLastError());
+      RGC_CUDA(cudaEventRecord(c.ev[3], c.stream));
+      count_launch(3);
+      return RGC_OK;
+    }
+    sync_literal_kernel<<<dim3((unsigned)nbx, (unsigned)nslices, (unsigned)nbatch), kLitThreads, 0, c.stream>>>(P);
     RGC_CUDA(cudaGetLastError());
     RGC_CUDA(cudaEventRecord(c.ev[3], c.stream));
-    literal_reduce_kernel<<<(unsigned)((nbins + 127) / 128), 128, 0, c.stream>>>(
+    literal_reduce_kernel<<<dim3((unsigned)((nbins + 127) / 128), (unsigned)nbatch), 128, 0, c.stream>>>(
       P.partials, nslices, (int)nbins, d_out);
     RGC_CUDA(cudaGetLastError());
     count_launch(3);

@@ -736,21 +736,28 @@ extern "C" {
     return RGC_OK;
   }
 
-  int rgc_sync_spectrum_dist(const float* gbeta, const float* f, size_t ndist,
-                             int islog_bins_prtls, const float* bins_e_syn, size_t nbins,
-                             const float* tab_x, const float* tab_y, size_t tab_n, float g_syn,
-                             float e_syn_at_g_syn, float* out_spec, double* out_spec64) {
+  int rgc_sync_spectrum_dist_batch(const float* gbeta, const float* f, size_t nbatch, size_t ndist,
+                                   int islog_bins_prtls, const float* bins_e_syn, size_t nbins,
+                                   const float* tab_x, const float* tab_y, size_t tab_n,
+                                   float g_syn, float e_syn_at_g_syn, int mode, float* out_spec,
+                                   double* out_spec64) {
     RGC_REQUIRE_INIT();
-    if (nbins == 0) {
+    if (nbins == 0 || nbatch == 0) {
       return RGC_OK;
     }
     if (ndist > (std::size_t)1 << 30 || nbins > (std::size_t)1 << 30) {
       return fail(RGC_ERR_INVALID, "SynchrotronSpectrumFromDist: grid too large");
     }
+    if (mode < -1 || mode > 1) {
+      return fail(RGC_ERR_INVALID, "rgc_sync_spectrum_dist_batch: mode must be -1, 0 or 1");
+    }
     auto& c = ctx();
     if (tab_n < 2) {
       return fail(RGC_ERR_INVALID, "F table needs at least 2 points");
     }
+    // measured on B200 (profiles/r2_fromdist_batch.txt): the kernel-matrix build costs one
+    // literal pass over G x M pairs, so the contraction pays from ~64 distributions on (kernel time; 16384: 0.24 ms against 5.2 ms)
+    const bool contract = mode == 1 || (mode == -1 && nbatch >= 64);
     // per distribution bin, on the host (ndist values): e_peak exactly as the reference
     // forms it in float (synchrotron.hpp:78-79); the term ((f * e_syn) [* gbeta]) * F is
     // formed per pair by the literal kernel (synchrotron.hpp:89-93)
@@ -760,27 +767,35 @@ extern "C" {
       ep[g]          = e_syn_at_g_syn * gb * gb / (g_syn * g_syn);
     }
     void* result = nullptr;
-    RGC_TRY(ensure_result(nbins * sizeof(double), &result));
+    RGC_TRY(ensure_result(nbatch * nbins * sizeof(double), &result));
     double* d_out = static_cast<double*>(result);
     RGC_CUDA(cudaEventRecord(c.ev[0], c.stream));
     if (ndist == 0) {
-      RGC_CUDA(cudaMemsetAsync(d_out, 0, nbins * sizeof(double), c.stream));
+      RGC_CUDA(cudaMemsetAsync(d_out, 0, nbatch * nbins * sizeof(double), c.stream));
       RGC_CUDA(cudaEventRecord(c.ev[2], c.stream));
       RGC_CUDA(cudaEventRecord(c.ev[3], c.stream));
     } else {
       RGC_TRY(run_spectrum_literal(nullptr, ndist, 1.0f, g_syn, e_syn_at_g_syn, ep.data(), f,
                                    islog_bins_prtls ? gbeta : nullptr, bins_e_syn, nbins, tab_x,
-                                   tab_y, tab_n, d_out));
+                                   tab_y, tab_n, d_out, nbatch, contract));
     }
-    std::vector<double> acc(nbins);
-    RGC_CUDA(cudaMemcpyAsync(acc.data(), d_out, nbins * sizeof(double), cudaMemcpyDeviceToHost,
+    std::vector<double> acc(nbatch * nbins);
+    RGC_CUDA(cudaMemcpyAsync(acc.data(), d_out, acc.size() * sizeof(double), cudaMemcpyDeviceToHost,
                              c.stream));
     RGC_CUDA(cudaEventRecord(c.ev[1], c.stream));
     RGC_CUDA(cudaStreamSynchronize(c.stream));
     RGC_CUDA(cudaEventElapsedTime(&c.last_ms[0], c.ev[0], c.ev[1]));
     RGC_CUDA(cudaEventElapsedTime(&c.last_ms[1], c.ev[2], c.ev[3]));
-    finish_spectrum(acc, nbins, out_spec, out_spec64);
+    finish_spectrum(acc, nbatch * nbins, out_spec, out_spec64);
     return RGC_OK;
+  }
+
+  int rgc_sync_spectrum_dist(const float* gbeta, const float* f, size_t ndist,
+                             int islog_bins_prtls, const float* bins_e_syn, size_t nbins,
+                             const float* tab_x, const float* tab_y, size_t tab_n, float g_syn,
+                             float e_syn_at_g_syn, float* out_spec, double* out_spec64) {
+    return rgc_sync_spectrum_dist_batch(gbeta, f, 1, ndist, islog_bins_prtls, bins_e_syn, nbins, tab_x,
+                                        tab_y, tab_n, g_syn, e_syn_at_g_syn, 0, out_spec, out_spec64);
   }
 
 } // extern "C"

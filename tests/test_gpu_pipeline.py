@@ -38,10 +38,14 @@ def test_pipeline_matches_oracle_and_sequential(cabi, port, tmp_path):
             _, want_h, _ = port.energy_distribution(*U, gbins, True, True)
             nz = want_h > 0
             assert np.max(np.abs(r.distribution[nz] - want_h[nz]) / want_h[nz]) < 1e-5
+            # the batched SynchrotronSpectrumFromDist of that distribution (4 items: literal terms)
+            _, want_d = port.sync_spectrum_dist(gbins, r.distribution, True, pbins, consts[1], consts[2])
+            assert synth.rel_err(r.spectrum_from_dist, want_d.astype(np.float32), floor_frac=0.0) < 1.2e-7
     with cabi.H5File(str(out), "r") as f:
         names = set(f.list("/"))
         assert {"sync_photon_energy_mec2", "sync_intensity_e-_3", "distribution_e+_4",
-                "gammaM1_e-_4"} <= names
+                "gammaM1_e-_4", "sync_intensity_dist_e-_3"} <= names
+        assert np.array_equal(f.read("sync_intensity_dist_e+_4"), rep.by(4, "e+").spectrum_from_dist)
         assert np.array_equal(f.read("sync_intensity_e+_4"), rep.by(4, "e+").spectrum)
         assert np.array_equal(f.read("sync_photon_energy_mec2"), pbins)
 
