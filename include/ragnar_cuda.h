@@ -283,6 +283,12 @@ int rgc_last_pair_lane_evals(double* lane_evals);
  * cell pair is not identically zero — what an ideal kernel would have to evaluate (the
  * whole-step roofline of bench.py); counted on the device by pair_moments_kernel. */
 int rgc_last_pair_ontable_evals(double* evals);
+/* How the bucket sort of the hinge pipeline ranks particles: 1 = one shared-memory atomic per
+ * particle, after a probe kernel verified ON THIS DEVICE that the lanes of one instruction
+ * hitting one address are served in lane order (what makes results bitwise reproducible);
+ * 0 = the probe failed, ranking by ballots (order fixed by construction); -1 = no hinge call
+ * yet.  RGC_SORT_RANK=ballot forces 0, RGC_SORT_RANK=atomic skips the probe. */
+int rgc_sort_rank_mode(int* mode);
 
 /* Roofline denominators measured on the device, on the compute stream (bench
  * harness only; MEASURED_PEAKS.json has no FP32 / shared-memory entry).

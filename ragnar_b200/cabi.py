@@ -86,6 +86,7 @@ SIGNATURES = {
     "rgc_trim_memory": (C.c_int, []),
     "rgc_last_pair_lane_evals": (C.c_int, [_f64p]),
     "rgc_last_pair_ontable_evals": (C.c_int, [_f64p]),
+    "rgc_sort_rank_mode": (C.c_int, [C.POINTER(C.c_int)]),
     "rgc_comm_exchange_kind": (C.c_int, [C.POINTER(C.c_int)]),
     "rgc_measure_peak": (C.c_int, [C.c_int, _f64p, _f64p]),
     "rgc_h5_open": (C.c_int, [C.c_char_p, C.c_int, _vpp]),
@@ -198,6 +199,13 @@ def comm_exchange_kind() -> str:
     k = C.c_int()
     check(lib().rgc_comm_exchange_kind(C.byref(k)))
     return {0: "single rank", 1: "ncclAllReduce", 2: "peer-store exchange over NVLink"}[k.value]
+
+
+def sort_rank_mode() -> int:
+    """1: atomic ranking verified by the on-device probe; 0: ballot ranking; -1: not decided yet"""
+    m = C.c_int()
+    check(lib().rgc_sort_rank_mode(C.byref(m)))
+    return m.value
 
 
 def trim_memory() -> None:

@@ -150,6 +150,7 @@ namespace rgc {
   int  collect_pair_times(float* main_ms);
   bool pair_single_pass(std::size_t n); // n particles fit one pipeline pass
   void pair_release_plans();            // frees the cached device plans (rgc_finalize)
+  int  pair_rank_mode(); // verdict of the rank-order probe: -1 not run, 0 ballots, 1 atomics
   // d_acc[binmap[s]] += src[s] for every slot with binmap[s] >= 0
   int  launch_scatter_add(const double* src, const int* binmap, int nslots, double* d_acc);
   // literal evaluation (rgc_sync_literal.cu): the reference's float term per pair, summed

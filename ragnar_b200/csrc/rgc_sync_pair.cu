@@ -289,8 +289,10 @@ namespace rgc {
     } while (!ok);
   }
 
-  // Lanes holding the same 11-bit key, from 11 ballots (MATCH.ANY takes several
-  // hundred cycles when most of a warp's keys differ, which is the normal case here)
+  // Lanes holding the same key, from one ballot per key bit (MATCH.ANY takes several
+  // hundred cycles when most of a warp's keys differ, which is the normal case here).
+  // Valid keys are < 1024 (kPMaxBuckets); kInvalidKey has all low bits set, so 11 bits
+  // always separate it from every bucket.
   __device__ __forceinline__ unsigned match_key11(unsigned key) {
     unsigned m = 0xffffffffu;
 #pragma unroll
@@ -300,6 +302,39 @@ namespace rgc {
       m &= bit ? bal : ~bal;
     }
     return m;
+  }
+
+  // ---- probe behind the default ranking of the sort kernel.  sync_sort_kernel<true> takes a
+  // particle's rank among its warp's particles of the same bucket from the return value of one
+  // shared-memory atomicAdd on a warp-private cursor.  The CUDA programming model does not say
+  // in which order the lanes of ONE instruction that hit the same address are served; the
+  // result is reproducible only if that order is a fixed function of the lane ids.  This
+  // kernel checks exactly that on the device in use (8 warps with private cursors and random
+  // keys, as in the sort kernel, many rounds): ranks of same-key lanes must ascend with the
+  // lane id.  One violation and the library ranks by ballots for the rest of the process
+  // (order fixed by construction, ~0.3 ms per 1e8 particles slower).
+  __global__ void __launch_bounds__(kPThreads)
+    rank_order_probe_kernel(int rounds, unsigned seed, int* __restrict__ violations) {
+    __shared__ int cur[kPWarps][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned  x    = seed ^ (blockIdx.x * 2654435761u) ^ (threadIdx.x * 40503u);
+    int       bad  = 0;
+    for (int r = 0; r < rounds; ++r) {
+      cur[warp][lane]      = 0;
+      cur[warp][lane + 32] = 0;
+      __syncwarp();
+      x = x * 1664525u + 1013904223u;
+      // few distinct keys: many same-address lanes per instruction
+      const unsigned key = (x >> 24) % (1u + (unsigned)(r % 24));
+      const int      rk  = atomicAdd(&cur[warp][key], 1);
+      const unsigned same = __match_any_sync(0xffffffffu, key);
+      const int      want = __popc(same & ((1u << lane) - 1u));
+      bad += rk != want;
+      __syncwarp();
+    }
+    if (bad) {
+      atomicAdd(violations, bad);
+    }
   }
 
   // Exclusive scans over the buckets, by one CTA of kPThreads threads:
@@ -1159,6 +1194,7 @@ namespace rgc {
   }
 
   static double2* g_log_tab = nullptr;
+  static int g_rank_order_ok = -1; // -1 unknown, 0 lanes are NOT served in lane order, 1 verified
 
   static int ensure_log_table(const double2** out) {
     if (!g_log_tab) {
@@ -1185,7 +1221,7 @@ namespace rgc {
       }
     }
     plan_cache().clear();
-
+    g_rank_order_ok = -1;
   }
 
   static int cached_pair_plan(const TablePlan& tp, const float* bins_e_syn,
@@ -1238,6 +1274,28 @@ namespace rgc {
     *out = &cache.back();
     return RGC_OK;
   }
+
+  // Runs rank_order_probe_kernel once per process (per device context) and remembers the verdict.
+  static int rank_order_verified(bool* ok) {
+    if (g_rank_order_ok < 0) {
+      auto& c       = ctx();
+      void* scratch = nullptr; // (laid out anew by the caller right after)
+      RGC_TRY(ensure_scratch(64, &scratch));
+      int* d_bad = static_cast<int*>(scratch);
+      RGC_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), c.stream));
+      rank_order_probe_kernel<<<2 * c.sm_count, kPThreads, 0, c.stream>>>(256, 0x9e3779b9u, d_bad);
+      RGC_CUDA(cudaGetLastError());
+      count_launch(1);
+      int bad = 0;
+      RGC_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+      RGC_CUDA(cudaStreamSynchronize(c.stream));
+      g_rank_order_ok = bad == 0 ? 1 : 0;
+    }
+    *ok = g_rank_order_ok == 1;
+    return RGC_OK;
+  }
+
+  int pair_rank_mode() { return g_rank_order_ok; }
 
   // particles per pipeline pass (bounds the staged and sorted arrays: 18 B per particle)
   static std::size_t pair_pass_max() {
@@ -1299,8 +1357,12 @@ namespace rgc {
     // bounded (18 B per particle); pass results are summed on the host in pass order
     const std::size_t chunk_max = pair_pass_max();
     const std::size_t cnt0      = std::min(n, chunk_max);
-    const char* sr          = std::getenv("RGC_SORT_RANK"); // "ballot": guaranteed-order ranking
-    const bool  atomic_rank = !(sr && std::strcmp(sr, "ballot") == 0);
+    // "ballot": ranking whose order is fixed by construction; "atomic": skip the probe
+    const char* sr          = std::getenv("RGC_SORT_RANK");
+    bool        atomic_rank = !(sr && std::strcmp(sr, "ballot") == 0);
+    if (atomic_rank && !(sr && std::strcmp(sr, "atomic") == 0)) {
+      RGC_TRY(rank_order_verified(&atomic_rank));
+    }
     const int sort_ctas_per_sm = 2;
     const char* pm       = std::getenv("RGC_PROLOGUE_MINB"); // tuning knob: prologue CTAs per SM
     const int   pro_minb = (pm && std::atoi(pm) == 4) ? 4 : 3;

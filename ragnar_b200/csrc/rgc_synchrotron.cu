@@ -728,6 +728,13 @@ extern "C" {
     return RGC_OK;
   }
 
+  int rgc_sort_rank_mode(int* mode) {
+    if (mode) {
+      *mode = pair_rank_mode();
+    }
+    return RGC_OK;
+  }
+
   int rgc_last_pair_ontable_evals(double* evals) {
     RGC_REQUIRE_INIT();
     if (evals) {

@@ -226,6 +226,9 @@ def test_repeatable(cabi, hinge):
     b = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)[1]
     assert np.array_equal(a, b), "fixed-order reductions: bitwise reproducible"
     assert cabi.launch_count() > 0
+    # the default ranking of the sort kernel is only used after the on-device probe verified
+    # that same-address shared atomics of one instruction are served in lane order
+    assert cabi.sort_rank_mode() == 1
 
 
 @pytest.mark.parametrize("nbins,lo,hi", [(200, 0.01, 1e5), (1000, 1e-3, 1e6), (5, 1.0, 10.0),
