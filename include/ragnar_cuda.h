@@ -231,6 +231,17 @@ int rgc_sync_spectrum_particles(const rgc_particles_t* p, size_t nactive,
                                 const float* bins_e_syn, size_t nbins, const float* tab_x,
                                 const float* tab_y, size_t tab_n, float B0, float g_syn,
                                 float e_syn_at_g_syn, float* out_spec, double* out_spec64);
+/* Particles.energyDistribution + SynchrotronSpectrum_<D>D of the same particles in one call — what
+ * the batched driver (legacy/simulation.cpp.bak:67-219, ragnar_b200/pipeline.py) does per species.
+ * The histogram's kernels and its all-reduce are enqueued without a wait, the spectrum pipeline
+ * follows on the same stream and both results are collected after one synchronisation: the
+ * same kernels as the two separate calls, bit-identical results, one host round trip less.
+ * out_hist / out_hist64: as rgc_energy_histogram (no counts output). */
+int rgc_hist_and_spectrum(const rgc_particles_t* p, size_t nactive, const float* gbins, size_t ng,
+                          int log_spaced, int fourvel, float* out_hist, double* out_hist64,
+                          const float* bins_e_syn, size_t nbins, const float* tab_x,
+                          const float* tab_y, size_t tab_n, float B0, float g_syn,
+                          float e_syn_at_g_syn, float* out_spec, double* out_spec64);
 
 /* SynchrotronSpectrumFromDist + sync::KernelFromDist —
  * src/physics/synchrotron.cpp:69-105, src/physics/synchrotron.hpp:41-96.

@@ -75,6 +75,8 @@ SIGNATURES = {
                                        _f64p]),
     "rgc_sync_spectrum_particles": (C.c_int, [_vp, _sz, _f32p, _sz, _f32p, _f32p, _sz,
                                               C.c_float, C.c_float, C.c_float, _f32p, _f64p]),
+    "rgc_hist_and_spectrum": (C.c_int, [_vp, _sz, _f32p, _sz, C.c_int, C.c_int, _f32p, _f64p, _f32p, _sz,
+                                        _f32p, _f32p, _sz, C.c_float, C.c_float, C.c_float, _f32p, _f64p]),
     "rgc_sync_spectrum_dist": (C.c_int, [_f32p, _f32p, _sz, C.c_int, _f32p, _sz, _f32p, _f32p,
                                          _sz, C.c_float, C.c_float, _f32p, _f64p]),
     "rgc_sync_spectrum_dist_batch": (C.c_int, [_f32p, _f32p, _sz, _sz, C.c_int, _f32p, _sz, _f32p, _f32p,
@@ -468,6 +470,22 @@ def sync_spectrum_particles(p: Particles, bins_e_syn, B0, g_syn, e_at, table=Non
                                             len(bins), _ptr(tx), _ptr(ty), len(tx), B0, g_syn,
                                             e_at, _ptr(s32), _ptr(s64, _f64p)))
     return s32, s64
+
+
+def hist_and_spectrum(p: Particles, gamma_bins, log_spaced: bool, fourvel: bool, bins_e_syn, B0, g_syn,
+                      e_at, table=None, nactive=None):
+    """energy histogram + particle spectrum in one call (kernels back to back on the stream, one
+    wait) -> (hist f32, hist f64, spec f32, spec f64)"""
+    gb, bins = _f32(gamma_bins), _f32(bins_e_syn)
+    tx, ty = table if table is not None else tabulate_ffunc()
+    tx, ty = _f32(tx), _f32(ty)
+    h32, h64 = np.zeros(len(gb), np.float32), np.zeros(len(gb), np.float64)
+    s32, s64 = np.zeros(len(bins), np.float32), np.zeros(len(bins), np.float64)
+    check(lib().rgc_hist_and_spectrum(p.h, p.n if nactive is None else nactive, _ptr(gb), len(gb),
+                                      int(log_spaced), int(fourvel), _ptr(h32), _ptr(h64, _f64p),
+                                      _ptr(bins), len(bins), _ptr(tx), _ptr(ty), len(tx), B0, g_syn, e_at,
+                                      _ptr(s32), _ptr(s64, _f64p)))
+    return h32, h64, s32, s64
 
 
 def sync_spectrum_dist(gbeta, f, islog, bins_e_syn, g_syn, e_at, table=None):

@@ -30,7 +30,7 @@
 // 16-byte evict-first loads); everything else stays on chip.
 //
 // Compiled with -fmad=false (Usqr must not be contracted into FMAs).
-#include "rgc_internal.hpp"
+#include "rgc_hist_device.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -40,84 +40,14 @@
 
 namespace rgc {
 
-  constexpr int kHThreads       = 256;
-  constexpr int kHWarps         = kHThreads / 32;
-  constexpr int kPerThread      = 8;                     // particles per thread per tile
-  constexpr int kHTile          = kHThreads * kPerThread; // 2048
-  constexpr int kWeightBits     = 20;
-  constexpr unsigned kWeightCap = 1u << 21; // larger quantised weights take the slow path
-
-  struct HistParams {
-    const float*  u[3];
-    std::size_t   nprtl;
-    int           n;          // bins
-    int           ncopies;    // private shared-memory copies (divides kHWarps)
-    int           flush_every; // tiles between u32 -> u64 weight flushes
-    const float4* binfo;      // per bin: thr[b], thr[b+1], weight scale, 1/scale (0 = slow path)
-    float         estA, estB; // bin guess = estA * log2(X) + estB
-    int           est_ok;
-    // outputs
-    unsigned long long* counts;  // [n]
-    unsigned long long* wfx;     // [n] fixed-point weight sums
-    double*             wslow;   // [n] fp64 slow-path weight sums (global atomics)
-    double*             clamp_part; // [gridDim][2] per-CTA weight sums of bins 0 and n-1
-  };
-
-  __device__ __forceinline__ int search_bin(const float4* binfo, int n, float U) {
-    if (U != U) {
-      return n - 1; // x86 NaN -> size_t conversion as in the reference build
-    }
-    int lo = 0, hi = n - 1; // largest b with U >= thr[b]; thr[0] = 0
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (U >= binfo[mid].x) {
-        lo = mid;
-      } else {
-        hi = mid - 1;
-      }
-    }
-    return lo;
-  }
-
   template <bool FOURVEL, bool WEIGHTED, bool COUNTS>
   __global__ void __launch_bounds__(kHThreads)
     energy_hist_kernel(const __grid_constant__ HistParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = P.n;
-    float4*   binfo = reinterpret_cast<float4*>(smem_raw);
-    unsigned long long* bfx = reinterpret_cast<unsigned long long*>(binfo + n);
-    double*   bslow = reinterpret_cast<double*>(bfx + n);
-    unsigned* wcnt  = reinterpret_cast<unsigned*>(bslow + n);          // [ncopies][n]
-    unsigned* wfx   = wcnt + (COUNTS ? (std::size_t)P.ncopies * n : 0); // [ncopies][n]
-
-    const int tid  = threadIdx.x;
-    const int warp = tid >> 5;
-    const int copy = warp % P.ncopies;
-
-    for (int i = tid; i < n; i += kHThreads) {
-      binfo[i] = P.binfo[i];
-      bfx[i]   = 0ull;
-      bslow[i] = 0.0;
-    }
-    for (int i = tid; i < P.ncopies * n; i += kHThreads) {
-      if (COUNTS) {
-        wcnt[i] = 0u;
-      }
-      if (WEIGHTED) {
-        wfx[i] = 0u;
-      }
-    }
-    __syncthreads();
-
-    unsigned* my_cnt = wcnt + (std::size_t)copy * n;
-    unsigned* my_fx  = wfx + (std::size_t)copy * n;
-
-    unsigned long long lo_cnt = 0, hi_cnt = 0;
-    double             lo_sum = 0.0, hi_sum = 0.0;
-    const float        nm1f   = (float)(n - 1);
-
+    HistAccum<FOURVEL, WEIGHTED, COUNTS> acc;
+    acc.init(smem_raw, P);
+    const int         tid    = threadIdx.x;
     const std::size_t ntiles = (P.nprtl + kHTile - 1) / kHTile;
-    int               since_flush = 0;
     for (std::size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const std::size_t base = tile * kHTile;
       float4            ux[kPerThread / 4], uy[kPerThread / 4], uz[kPerThread / 4];
@@ -132,8 +62,6 @@ namespace rgc {
           ux[h] = uy[h] = uz[h] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      float    lo_f = 0.0f, hi_f = 0.0f;
-      unsigned lo_c = 0, hi_c = 0;
       // full tiles (all but the last) carry no per-particle bounds checks
       const bool full = base + kHTile <= P.nprtl;
 #pragma unroll
@@ -147,128 +75,12 @@ namespace rgc {
           if (!full && i0 + k >= P.nprtl) {
             continue;
           }
-          // reference particles.cpp:228-230, float, left to right, unfused
-          const float U = (px[k] * px[k] + py[k] * py[k]) + pz[k] * pz[k];
-          const float X = FOURVEL ? U : 1.0f + U;
-          int         idx;
-          float4      info;
-          bool        ok = false;
-          if (P.est_ok) {
-            float g = fmaf(P.estA, __log2f(X), P.estB);
-            g       = fminf(fmaxf(g, 0.0f), nm1f);
-            idx     = (int)g;
-            info    = binfo[idx];
-            ok      = (U >= info.x) && (!(U >= info.y) || idx == n - 1);
-          }
-          if (!ok) {
-            idx  = search_bin(binfo, n, U);
-            info = binfo[idx];
-          }
-          float w = 0.0f;
-          if (WEIGHTED) {
-            w = rsqrtf(X); // 1/energy; the reference rounds 1.0/energy to float
-          }
-          if (idx == 0) {
-            lo_c += 1u;
-            lo_f += w;
-          } else if (idx == n - 1) {
-            hi_c += 1u;
-            hi_f += w;
-          } else {
-            if (COUNTS) {
-              atomicAdd(&my_cnt[idx], 1u);
-            }
-            if (WEIGHTED) {
-              const float scaled = w * info.z;
-              if (info.z > 0.0f && scaled < (float)kWeightCap) {
-                atomicAdd(&my_fx[idx], __float2uint_rn(scaled));
-              } else {
-                atomicAdd(&bslow[idx], (double)w);
-              }
-            }
-          }
+          acc.add(P, px[k], py[k], pz[k]);
         }
       }
-      lo_cnt += lo_c;
-      hi_cnt += hi_c;
-      if (WEIGHTED) {
-        lo_sum += (double)lo_f;
-        hi_sum += (double)hi_f;
-        if (++since_flush == P.flush_every) {
-          since_flush = 0;
-          __syncthreads();
-          for (int i = tid; i < n; i += kHThreads) {
-            unsigned long long s = 0;
-            for (int cpy = 0; cpy < P.ncopies; ++cpy) {
-              s += wfx[(std::size_t)cpy * n + i];
-              wfx[(std::size_t)cpy * n + i] = 0u;
-            }
-            bfx[i] += s;
-          }
-          __syncthreads();
-        }
-      }
+      acc.end_tile(P);
     }
-
-    // ---- CTA epilogue: private copies -> global u64 (exact, order independent)
-    __syncthreads();
-    for (int i = tid; i < n; i += kHThreads) {
-      unsigned long long c = 0, f = bfx[i];
-      for (int cpy = 0; cpy < P.ncopies; ++cpy) {
-        if (COUNTS) {
-          c += wcnt[(std::size_t)cpy * n + i];
-        }
-        if (WEIGHTED) {
-          f += wfx[(std::size_t)cpy * n + i];
-        }
-      }
-      if (COUNTS && c) {
-        atomicAdd(&P.counts[i], c);
-      }
-      if (WEIGHTED && f) {
-        atomicAdd(&P.wfx[i], f);
-      }
-      if (WEIGHTED && bslow[i] != 0.0) {
-        atomicAdd(&P.wslow[i], bslow[i]);
-      }
-    }
-    // clamp bins: block reduction of the per-thread registers
-    __syncthreads();
-    unsigned long long* rc = reinterpret_cast<unsigned long long*>(smem_raw); // reuse
-    double*             rs = reinterpret_cast<double*>(rc + 2 * kHWarps);
-    for (int off = 16; off > 0; off >>= 1) {
-      lo_cnt += __shfl_down_sync(0xffffffffu, lo_cnt, off);
-      hi_cnt += __shfl_down_sync(0xffffffffu, hi_cnt, off);
-      lo_sum += __shfl_down_sync(0xffffffffu, lo_sum, off);
-      hi_sum += __shfl_down_sync(0xffffffffu, hi_sum, off);
-    }
-    if ((tid & 31) == 0) {
-      rc[warp * 2 + 0] = lo_cnt;
-      rc[warp * 2 + 1] = hi_cnt;
-      rs[warp * 2 + 0] = lo_sum;
-      rs[warp * 2 + 1] = hi_sum;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned long long c0 = 0, c1 = 0;
-      double             s0 = 0.0, s1 = 0.0;
-      for (int wq = 0; wq < kHWarps; ++wq) {
-        c0 += rc[wq * 2 + 0];
-        c1 += rc[wq * 2 + 1];
-        s0 += rs[wq * 2 + 0];
-        s1 += rs[wq * 2 + 1];
-      }
-      // counts of the clamp bins are needed even when COUNTS is off only for the
-      // unweighted histogram value, which is requested with COUNTS on
-      if (c0) {
-        atomicAdd(&P.counts[0], c0);
-      }
-      if (c1) {
-        atomicAdd(&P.counts[n - 1], c1);
-      }
-      P.clamp_part[(std::size_t)blockIdx.x * 2 + 0] = s0;
-      P.clamp_part[(std::size_t)blockIdx.x * 2 + 1] = s1;
-    }
+    acc.finish(P, smem_raw);
   }
 
   // wslow[0] += sum_cta clamp[cta][0], wslow[n-1] += sum_cta clamp[cta][1]: lane-strided
@@ -393,6 +205,122 @@ namespace rgc {
     return hp;
   }
 
+  static std::size_t align256(std::size_t x) { return (x + 255) & ~std::size_t(255); }
+
+  // device bytes of one job: [counts | wfx | wslow] (one exchange), clamp partials, bin info
+  std::size_t hist_job_bytes(std::size_t n, int sm_count) {
+    return align256(3 * n * 8) + align256((std::size_t)sm_count * 8 * 2 * sizeof(double)) +
+           align256(n * sizeof(float4));
+  }
+
+  int hist_enqueue(const rgc_particles* p, std::size_t nactive, const float* bins, std::size_t n,
+                   bool weighted, bool fv, bool want_counts, char* dev, HistJob& job) {
+    auto& c = ctx();
+    // reference particles.cpp:200-216: bins' min / max, not first / last
+    float emin = std::numeric_limits<float>::max(), emax = std::numeric_limits<float>::lowest();
+    for (std::size_t i = 0; i < n; ++i) {
+      emin = bins[i] < emin ? bins[i] : emin;
+      emax = bins[i] > emax ? bins[i] : emax;
+    }
+    // ---- threshold table, bin info and the bin-guess coefficients depend only on
+    // (bins, fourvel, log_spaced): built once (199 bisections through libm) and kept
+    const HistPlan& plan = hist_plan(bins, n, fv, weighted, emin, emax);
+    job.n         = n;
+    job.weighted  = weighted;
+    job.inv_scale = plan.inv_scale;
+    job.dev       = dev;
+    HistParams P {};
+    P.est_ok = plan.est_ok;
+    P.estA   = plan.estA;
+    P.estB   = plan.estB;
+    for (int d = 0; d < 3; ++d) {
+      P.u[d] = p->col[RGC_Q_U][d];
+    }
+    P.nprtl = nactive;
+    P.n     = (int)n;
+    // private copies: as many warps' worth as fit comfortably
+    want_counts      = want_counts || !weighted;
+    const int arrays = (want_counts ? 1 : 0) + (weighted ? 1 : 0);
+    int       ncopies = kHWarps;
+    while (ncopies > 1 && hist_smem_bytes((int)n, ncopies, arrays) > 48 * 1024) {
+      ncopies /= 2;
+    }
+    P.ncopies = ncopies;
+    // a copy receives (kHWarps/ncopies) * 32 * kPerThread quantised weights < 2^21 per tile
+    P.flush_every = std::max(1, (int)((1ull << 32) / ((unsigned long long)kWeightCap *
+                                                      (kHWarps / ncopies) * 32 * kPerThread)) - 1);
+    const std::size_t smem = std::max<std::size_t>(hist_smem_bytes((int)n, ncopies, arrays), 1024);
+
+    using kern_t = void (*)(HistParams);
+    kern_t kern  = nullptr;
+#define RGC_PICK(FV, W, C)                               \
+  if (fv == FV && weighted == W && want_counts == C) {   \
+    kern = energy_hist_kernel<FV, W, C>;                 \
+  }
+    RGC_PICK(true, true, true)
+    RGC_PICK(true, true, false)
+    RGC_PICK(true, false, true)
+    RGC_PICK(false, true, true)
+    RGC_PICK(false, true, false)
+    RGC_PICK(false, false, true)
+#undef RGC_PICK
+    if (smem > 48 * 1024) {
+      RGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    int per_sm = 0;
+    RGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kHThreads, smem));
+    per_sm = std::max(1, std::min(per_sm, 8));
+    const std::size_t ntiles = (nactive + kHTile - 1) / kHTile;
+    const int nctas = (int)std::min<std::size_t>((std::size_t)c.sm_count * per_sm,
+                                                 std::max<std::size_t>(ntiles, 1));
+    const std::size_t off_clamp = align256(3 * n * 8);
+    const std::size_t off_binfo = off_clamp + align256((std::size_t)c.sm_count * 8 * 2 * sizeof(double));
+    P.counts     = reinterpret_cast<unsigned long long*>(dev);
+    P.wfx        = reinterpret_cast<unsigned long long*>(dev + n * 8); // adjacent: [counts | wfx | wslow]
+    P.wslow      = reinterpret_cast<double*>(dev + 2 * n * 8);         // is ONE exchange
+    P.clamp_part = reinterpret_cast<double*>(dev + off_clamp);
+    P.binfo      = reinterpret_cast<const float4*>(dev + off_binfo);
+    RGC_TRY(copy_h2d(dev + off_binfo, plan.binfo.data(), n * sizeof(float4), c.stream));
+    RGC_CUDA(cudaMemsetAsync(dev, 0, off_binfo, c.stream));
+    RGC_CUDA(cudaEventRecord(c.ev[0], c.stream));
+    kern<<<nctas, kHThreads, smem, c.stream>>>(P);
+    RGC_CUDA(cudaGetLastError());
+    count_launch(1);
+    RGC_CUDA(cudaEventRecord(c.ev[1], c.stream));
+    // ---- combine on the device: the clamp bins' per-CTA partial sums are folded (fixed
+    // order) into the fp64 slow-path array; with a communicator, one exchange of
+    // [u64 counts | fixed-point sums | f64 slow path].  Integer sums are exact.
+    hist_fold_clamp_kernel<<<1, 32, 0, c.stream>>>(P.clamp_part, nctas, P.wslow, (int)n);
+    RGC_CUDA(cudaGetLastError());
+    count_launch(1);
+    return allreduce_sum_mixed(P.counts, 2 * n, n);
+  }
+
+  int hist_collect(const HistJob& job, float* out_hist, std::uint64_t* out_counts, double* out_sum64) {
+    auto&             c = ctx();
+    const std::size_t n = job.n;
+    std::vector<unsigned long long> raw(3 * n);
+    RGC_CUDA(cudaMemcpyAsync(raw.data(), job.dev, 3 * n * 8, cudaMemcpyDeviceToHost, c.stream));
+    RGC_CUDA(cudaStreamSynchronize(c.stream));
+    RGC_TRY(exchange_check());
+    const auto* counts = raw.data();
+    const auto* wfx    = raw.data() + n;
+    const auto* wslow  = reinterpret_cast<const double*>(raw.data() + 2 * n);
+    for (std::size_t b = 0; b < n; ++b) {
+      const double sum = job.weighted ? (double)wfx[b] * job.inv_scale[b] + wslow[b] : (double)counts[b];
+      if (out_sum64) {
+        out_sum64[b] = sum;
+      }
+      if (out_hist) {
+        out_hist[b] = (float)sum;
+      }
+      if (out_counts) {
+        out_counts[b] = counts[b];
+      }
+    }
+    return RGC_OK;
+  }
+
 } // namespace rgc
 
 using namespace rgc;
@@ -415,133 +343,17 @@ extern "C" {
     if (n > 5000) {
       return fail(RGC_ERR_INVALID, "energy histogram supports at most 5000 bins (got %zu)", n);
     }
-    auto& c = ctx();
-    // reference particles.cpp:200-216: bins' min / max, not first / last
-    float emin = std::numeric_limits<float>::max(), emax = std::numeric_limits<float>::lowest();
-    for (std::size_t i = 0; i < n; ++i) {
-      emin = bins[i] < emin ? bins[i] : emin;
-      emax = bins[i] > emax ? bins[i] : emax;
-    }
-    const bool fv       = fourvel != 0;
-    const bool weighted = log_spaced != 0;
-    // ---- threshold table, bin info and the bin-guess coefficients depend only on
-    // (bins, fourvel, log_spaced): built once (199 bisections through libm) and kept
-    const HistPlan& plan = hist_plan(bins, n, fv, weighted, emin, emax);
-    const std::vector<float4>& binfo     = plan.binfo;
-    const std::vector<double>& inv_scale = plan.inv_scale;
-    HistParams P {};
-    P.est_ok = plan.est_ok;
-    P.estA   = plan.estA;
-    P.estB   = plan.estB;
-    for (int d = 0; d < 3; ++d) {
-      P.u[d] = p->col[RGC_Q_U][d];
-    }
-    P.nprtl = nactive;
-    P.n     = (int)n;
-    // private copies: as many warps' worth as fit comfortably
-    const bool want_counts = !weighted || out_counts != nullptr;
-    const int  arrays      = (want_counts ? 1 : 0) + (weighted ? 1 : 0);
-    int        ncopies     = kHWarps;
-    auto smem_for = [&](int copies) {
-      return n * (sizeof(float4) + 8 + 8) + (std::size_t)copies * arrays * n * 4;
-    };
-    while (ncopies > 1 && smem_for(ncopies) > 48 * 1024) {
-      ncopies /= 2;
-    }
-    P.ncopies = ncopies;
-    // a copy receives (kHWarps/ncopies) * 32 * kPerThread quantised weights < 2^21 per tile
-    P.flush_every = std::max(1, (int)((1ull << 32) / ((unsigned long long)kWeightCap *
-                                                      (kHWarps / ncopies) * 32 * kPerThread)) - 1);
-    const std::size_t smem = std::max<std::size_t>(smem_for(ncopies), 1024);
-
-    // ---- device scratch
-    const std::size_t ntiles = (nactive + kHTile - 1) / kHTile;
-    auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
-
-    using kern_t = void (*)(HistParams);
-    kern_t kern  = nullptr;
-#define RGC_PICK(FV, W, C)                               \
-  if (fv == FV && weighted == W && want_counts == C) {   \
-    kern = energy_hist_kernel<FV, W, C>;                 \
-  }
-    RGC_PICK(true, true, true)
-    RGC_PICK(true, true, false)
-    RGC_PICK(true, false, true)
-    RGC_PICK(false, true, true)
-    RGC_PICK(false, true, false)
-    RGC_PICK(false, false, true)
-#undef RGC_PICK
-    if (smem > 48 * 1024) {
-      RGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    int per_sm = 0;
-    RGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kHThreads, smem));
-    per_sm    = std::max(1, std::min(per_sm, 8));
-    int nctas = (int)std::min<std::size_t>((std::size_t)c.sm_count * per_sm,
-                                           std::max<std::size_t>(ntiles, 1));
-
-    const std::size_t off_binfo  = 0;
-    const std::size_t off_counts = align(off_binfo + n * sizeof(float4));
-    const std::size_t off_wfx    = off_counts + n * 8; // adjacent: one u64 all-reduce of 2n
-    const std::size_t off_wslow  = off_wfx + n * 8;     // adjacent too: [counts | wfx | wslow] is one exchange
-    const std::size_t off_clamp  = align(off_wslow + n * 8);
-    const std::size_t total      = off_clamp + (std::size_t)nctas * 2 * sizeof(double);
-    void*             scratch    = nullptr;
-    RGC_TRY(ensure_scratch(total, &scratch));
-    char* sbase  = static_cast<char*>(scratch);
-    P.binfo      = reinterpret_cast<const float4*>(sbase + off_binfo);
-    P.counts     = reinterpret_cast<unsigned long long*>(sbase + off_counts);
-    P.wfx        = reinterpret_cast<unsigned long long*>(sbase + off_wfx);
-    P.wslow      = reinterpret_cast<double*>(sbase + off_wslow);
-    P.clamp_part = reinterpret_cast<double*>(sbase + off_clamp);
-
-    RGC_CUDA(cudaMemcpyAsync(sbase + off_binfo, binfo.data(), n * sizeof(float4),
-                             cudaMemcpyHostToDevice, c.stream));
-    RGC_CUDA(cudaMemsetAsync(sbase + off_counts, 0, total - off_counts, c.stream));
-    RGC_CUDA(cudaEventRecord(c.ev[0], c.stream));
-    kern<<<nctas, kHThreads, smem, c.stream>>>(P);
-    RGC_CUDA(cudaGetLastError());
-    count_launch(1);
-    RGC_CUDA(cudaEventRecord(c.ev[1], c.stream));
-
-    // ---- combine on the device: the clamp bins' per-CTA partial sums are folded (fixed
-    // order) into the fp64 slow-path array; with a communicator, one fused group of two
-    // all-reduces (u64 counts + fixed-point sums, f64 slow path); then ONE D2H of
-    // [counts | fixed-point sums | fp64 slow path].  Integer sums are exact.
-    hist_fold_clamp_kernel<<<1, 32, 0, c.stream>>>(P.clamp_part, nctas, P.wslow, (int)n);
-    RGC_CUDA(cudaGetLastError());
-    count_launch(1);
-    RGC_TRY(allreduce_sum_mixed(P.counts, 2 * n, n));
-    std::vector<unsigned char> raw(off_clamp - off_counts);
-    RGC_CUDA(cudaMemcpyAsync(raw.data(), sbase + off_counts, raw.size(), cudaMemcpyDeviceToHost,
-                             c.stream));
-    RGC_CUDA(cudaStreamSynchronize(c.stream));
-    RGC_TRY(exchange_check());
-    const auto* counts = reinterpret_cast<const unsigned long long*>(raw.data());
-    const auto* wfx    = reinterpret_cast<const unsigned long long*>(raw.data() + (off_wfx - off_counts));
-    const auto* wslow  = reinterpret_cast<const double*>(raw.data() + (off_wslow - off_counts));
+    auto& c       = ctx();
+    void* scratch = nullptr;
+    RGC_TRY(ensure_scratch(hist_job_bytes(n, c.sm_count), &scratch));
+    HistJob job;
+    RGC_TRY(hist_enqueue(p, nactive, bins, n, log_spaced != 0, fourvel != 0, out_counts != nullptr,
+                         static_cast<char*>(scratch), job));
+    RGC_TRY(hist_collect(job, out_hist, out_counts, out_sum64));
     float ms = 0.f;
     RGC_CUDA(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]));
     c.last_ms[0] = ms;
     c.last_ms[1] = ms;
-
-    for (std::size_t b = 0; b < n; ++b) {
-      double sum;
-      if (weighted) {
-        sum = (double)wfx[b] * inv_scale[b] + wslow[b];
-      } else {
-        sum = (double)counts[b];
-      }
-      if (out_sum64) {
-        out_sum64[b] = sum;
-      }
-      if (out_hist) {
-        out_hist[b] = (float)sum;
-      }
-      if (out_counts) {
-        out_counts[b] = counts[b];
-      }
-    }
     return RGC_OK;
   }
 

@@ -45,7 +45,7 @@
 //
 // Compiled with -fmad=false: every FMA below is an explicit fmaf()/fma(), all
 // other float/double arithmetic is unfused like the reference's default build.
-#include "rgc_internal.hpp"
+#include "rgc_hist_device.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -718,6 +718,43 @@ extern "C" {
     std::vector<double> acc;
     RGC_TRY(run_spectrum(src, bins_e_syn, nbins, tab_x, tab_y, tab_n, true, acc));
     finish_spectrum(acc, nbins, out_spec, out_spec64);
+    return RGC_OK;
+  }
+
+  int rgc_hist_and_spectrum(const rgc_particles_t* p, size_t nactive, const float* gbins, size_t ng,
+                            int log_spaced, int fourvel, float* out_hist, double* out_hist64,
+                            const float* bins_e_syn, size_t nbins, const float* tab_x,
+                            const float* tab_y, size_t tab_n, float B0, float g_syn,
+                            float e_syn_at_g_syn, float* out_spec, double* out_spec64) {
+    RGC_REQUIRE_INIT();
+    if (!p || !p->allocated) {
+      return fail(RGC_ERR_INVALID, "Particles not allocated");
+    }
+    if (nactive > p->nalloc) {
+      return fail(RGC_ERR_INVALID, "nactive %zu exceeds allocation %zu", nactive, p->nalloc);
+    }
+    if (ng > 5000) {
+      return fail(RGC_ERR_INVALID, "energy histogram supports at most 5000 bins (got %zu)", ng);
+    }
+    // The histogram is enqueued (kernel, fold, exchange) without a wait, the spectrum pipeline
+    // runs right behind it on the same stream, and both results are collected after the
+    // spectrum's one synchronisation: the same kernels as the two separate entry points,
+    // bit-identical results, one host round trip less per species.  Its device arrays live in
+    // the result buffer, past the spectrum's part (the scratch is re-laid-out by the pipeline).
+    auto&   c = ctx();
+    HistJob job;
+    if (ng > 0) {
+      const std::size_t spec_bytes = (nbins * sizeof(double) + 24 + nbins * sizeof(float) + 255) & ~std::size_t(255);
+      void*             result     = nullptr;
+      RGC_TRY(ensure_result(spec_bytes + hist_job_bytes(ng, c.sm_count), &result));
+      RGC_TRY(hist_enqueue(p, nactive, gbins, ng, log_spaced != 0, fourvel != 0, false,
+                           static_cast<char*>(result) + spec_bytes, job));
+    }
+    RGC_TRY(rgc_sync_spectrum_particles(p, nactive, bins_e_syn, nbins, tab_x, tab_y, tab_n, B0, g_syn,
+                                        e_syn_at_g_syn, out_spec, out_spec64));
+    if (ng > 0) {
+      RGC_TRY(hist_collect(job, out_hist, nullptr, out_hist64));
+    }
     return RGC_OK;
   }
 

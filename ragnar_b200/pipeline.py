@@ -141,10 +141,9 @@ def process_steps(path: str, steps, species, photon_bins, gamma_bins, B0: float,
         prtls = reader.get()
         nxt = start(i + 1) if i + 1 < len(work) else None  # overlaps the compute below
         t0 = time.perf_counter()
-        hist, _, _ = cabi.energy_histogram(prtls, gamma_bins, gamma_bins_log_spaced, fourvel,
-                                           want_counts=False)
-        s32, s64 = cabi.sync_spectrum_particles(prtls, photon_bins, B0, g_syn, e_syn_at_g_syn,
-                                                table=table)
+        # one call: histogram and spectrum kernels back to back on the stream, one wait
+        hist, _, s32, s64 = cabi.hist_and_spectrum(prtls, gamma_bins, gamma_bins_log_spaced, fourvel,
+                                                   photon_bins, B0, g_syn, e_syn_at_g_syn, table=table)
         dt = time.perf_counter() - t0
         report.results.append(SpeciesResult(st, label, sp, prtls.n, hist, s32, s64,
                                             reader.seconds, dt))

@@ -348,3 +348,32 @@ def test_config3_at_1e7(cabi, port):
     _, counts, _ = cabi.energy_histogram(p, gb, log_spaced=False, fourvel=True)
     _, _, want_c = port.energy_distribution(*U, gb, False, True)
     assert counts.sum() == n and np.array_equal(counts, want_c)
+
+
+@pytest.mark.parametrize("fourvel", [True, False])
+@pytest.mark.parametrize("log_spaced", [True, False])
+def test_fused_histogram_and_spectrum_is_bit_identical(cabi, port, fourvel, log_spaced, monkeypatch):
+    """rgc_hist_and_spectrum (histogram enqueued ahead of the spectrum pipeline, one wait for
+    both): bit-identical to the two separate calls on the hinge pipeline, across several
+    passes and on the literal path"""
+    n = 700_000
+    U, E, B = synth.full3d(n, seed=31)
+    U[0][:5] = [0.0, 1e-9, 1e9, np.nan, np.inf]  # clamp bins, NaN -> last bin
+    p = _particles(cabi, U, E, B)
+    gb = cabi.logspace(1e-2, 1e3, 200) if log_spaced else cabi.linspace(0.5, 40, 64)
+    bins = cabi.logspace(0.01, 1e5, 200)
+    for nactive, passes in ((n, None), (n, "131072"), (5000, None)):
+        if passes:
+            monkeypatch.setenv("RGC_PAIR_PASS_MAX", passes)
+        h32, _, h64 = cabi.energy_histogram(p, gb, log_spaced, fourvel, nactive=nactive)
+        s32, s64 = cabi.sync_spectrum_particles(p, bins, 1.3, 2.0, 0.7, nactive=nactive)
+        f32, f64, t32, t64 = cabi.hist_and_spectrum(p, gb, log_spaced, fourvel, bins, 1.3, 2.0, 0.7, nactive=nactive)
+        if passes:
+            monkeypatch.delenv("RGC_PAIR_PASS_MAX")
+        assert np.array_equal(f64, h64, equal_nan=True) and np.array_equal(f32, h32, equal_nan=True)
+        assert np.array_equal(t64, s64, equal_nan=True) and np.array_equal(t32, s32, equal_nan=True)
+        assert f64[np.isfinite(f64)].sum() > 0
+    _, want_h, _ = port.energy_distribution(*U, gb, log_spaced, fourvel)
+    f32, f64, _, _ = cabi.hist_and_spectrum(p, gb, log_spaced, fourvel, bins, 1.3, 2.0, 0.7)
+    ok = np.isfinite(want_h) & (want_h > 0)
+    assert np.max(np.abs(f64[ok] - want_h[ok]) / want_h[ok]) < HIST_RTOL
