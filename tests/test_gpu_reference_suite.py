@@ -198,3 +198,28 @@ def test_module_vs_oracle_end_to_end(rg, port):
     counts = prtls.energyDistribution(gb).F().as_array()
     _, _, want_c = port.energy_distribution(*U, gb.as_array(), False, True)
     assert np.array_equal(counts, want_c.astype(np.float32))
+
+
+def test_module_edge_cases_follow_the_reference(rg, port):
+    """an empty photon Bins gives an empty Array1D (the reference launches N x 0 threads);
+    unallocated particles are N = 0: a zero spectrum, no error; the module's spectrum of a
+    small population is the reference's float value bit for bit (literal path)"""
+    from tests import synth
+
+    U, E, B = synth.full3d(3_000, seed=2)
+    prtls = rg.Particles_3D("e-")
+    prtls.fromArrays({f"{q}{d + 1}": a[d] for q, a in (("U", U), ("E", E), ("B", B)) for d in range(3)})
+    empty = rg.Bins(np.zeros(0, np.float32), rg.EnergyUnits.mec2)
+    assert rg.SynchrotronSpectrum_3D(prtls, empty, 1, 1, 1).as_array().shape == (0,)
+    bins = rg.Logbins(0.01, 1e5, 50, rg.EnergyUnits.mec2)
+    blank = rg.Particles_3D("none")
+    assert not blank.is_allocated()
+    assert not rg.SynchrotronSpectrum_3D(blank, bins, 1, 1, 1).as_array().any()
+    spec = rg.SynchrotronSpectrum_3D(prtls, bins, 1.3, 2.0, 0.7).as_array()
+    _, want = port.sync_spectrum_particles(U, E, B, bins.as_array(), 1.3, 2.0, 0.7)
+    assert np.array_equal(spec, want.astype(np.float32))
+    dist = rg.TabulatedDistribution(rg.Logbins(1, 100, 200), rg.PlawGenerator(-2, 1, 100))
+    b2 = rg.Logbins(0.01, 1e7, 200, rg.EnergyUnits.mec2)
+    s2 = rg.SynchrotronSpectrumFromDist(dist, b2, 1, 1).as_array()
+    _, w2 = port.sync_spectrum_dist(dist.EnergyBins().as_array(), dist.F().as_array(), True, b2.as_array(), 1, 1)
+    assert np.array_equal(s2, w2.astype(np.float32))
