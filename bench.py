@@ -641,6 +641,26 @@ def run_ours(args) -> None:
                         "into Logbins(1e-2, 1e3, 200)" if n == N_PER_GPU else f"{n} particles",
             "ms_per_launch": h2, "particles_per_s": n / (h2 * 1e-3),
             "hbm_GBps": n * 12 / (h2 * 1e-3) / 1e9, "frac_of_hbm_peak": n * 12 / (h2 * 1e-3) / 1e9 / hbm_peak}
+        # the gather kernel that serves tables / bin sets the hinge pipeline cannot take
+        # (DESIGN.md 3.3), forced onto the headline workload for a number to hold against it
+        p2.generate(0 if args.population == "config3" else 1, SEED, 0, 0, n, 1.0, 100.0)
+        cabi.synchronize()
+        os.environ["RGC_SPECTRUM_PATH"] = "gather"
+        try:
+            cabi.sync_spectrum_particles(p2, bins, *CONSTS, table=table)
+            gms = []
+            for _ in range(3):
+                cabi.sync_spectrum_particles(p2, bins, *CONSTS, table=table)
+                gms.append(cabi.last_kernel_times()[1])
+        finally:
+            os.environ.pop("RGC_SPECTRUM_PATH", None)
+        g_ms = statistics.mean(gms)
+        other["gather_fallback"] = {
+            "workload": f"the headline workload ({n} particles x {nbins} bins) forced onto sync_spectrum_kernel "
+                        "(RGC_SPECTRUM_PATH=gather)",
+            "ms_per_launch": g_ms, "evals_per_s": n * nbins / (g_ms * 1e-3),
+            "lds_gather_GBps": n * nbins * 8 / (g_ms * 1e-3) / 1e9,
+            "note": "8 B shared-memory gather + 7 issue slots per 32 evaluations; every pair is evaluated"}
         other["config0_fromdist"] = {
             "workload": "SynchrotronSpectrumFromDist: PlawGenerator(-2,1,100) on Logbins(1,100,200) -> "
                         "200 photon Logbins(0.01,1e7)", "evals": 40000,

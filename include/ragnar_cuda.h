@@ -76,7 +76,7 @@ const char* rgc_last_error(void);
 /* number of kernels this library has launched since rgc_init (bench evidence) */
 uint64_t rgc_launch_count(void);
 
-/* Particle columns are allocated from the device's stream-ordered memory pool and stay cached
+/* Particle columns are allocated from the library's own stream-ordered memory pool and stay cached
  * there when a container is released (re-creating a container per species / step then costs
  * no cudaMalloc / cudaFree); this returns the cached blocks to the device. */
 int rgc_trim_memory(void);

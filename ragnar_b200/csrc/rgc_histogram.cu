@@ -331,6 +331,7 @@ extern "C" {
                            int log_spaced, int fourvel, float* out_hist, uint64_t* out_counts,
                            double* out_sum64) {
     RGC_REQUIRE_INIT();
+    RGC_NVTX("ComputeEnergyDistribution");
     if (!p || !p->allocated) {
       return fail(RGC_ERR_INVALID, "Particles not allocated");
     }

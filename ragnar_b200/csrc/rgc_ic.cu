@@ -141,6 +141,7 @@ extern "C" {
                       size_t nsoft, const float* bins_e_ic, size_t nic, float* out_spec,
                       double* out_spec64) {
     RGC_REQUIRE_INIT();
+    RGC_NVTX("ICSpectrum");
     if (nic == 0) {
       return RGC_OK;
     }

@@ -6,6 +6,7 @@
 #include "ragnar_cuda.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only; a no-op unless a profiler is attached
 
 #include <atomic>
 #include <cstdarg>
@@ -49,6 +50,20 @@ namespace rgc {
     }                                                                               \
   } while (0)
 
+  // NVTX range over an entry point, named after the Kokkos kernel label it replaces
+  // (reference: "SynchrotronSpectrum" src/physics/synchrotron.cpp:92,131,
+  // "ComputeEnergyDistribution" src/containers/particles.cpp:225, "ICSpectrum"
+  // src/physics/ic.cpp:38, "Linspace"/"Logspace" src/utils/snippets.cpp:27,49, "XMinMax"
+  // src/containers/tabulation.cpp:89), so a timeline of this library reads like one of
+  // the reference's Kokkos-tools traces
+  struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&)            = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+  };
+#define RGC_NVTX(name) ::rgc::NvtxRange rgc_nvtx_range__ { name }
+
   // ----------------------------------------------------------------- context
   constexpr std::size_t kStageBytes = std::size_t(32) << 20; // per pinned stage
   constexpr int         kNumStages  = 4;
@@ -60,6 +75,8 @@ namespace rgc {
     std::size_t  hbm_bytes { 0 };
     cudaStream_t stream { nullptr };      // compute + ordered copies
     cudaStream_t copy_stream { nullptr }; // bulk H2D of particle columns
+    cudaMemPool_t column_pool { nullptr }; // stream-ordered pool of the particle columns (own pool:
+                                           // its unlimited release threshold touches nobody else)
     // pinned staging ring for pageable host sources
     void*       stage[kNumStages] {};
     cudaEvent_t stage_free[kNumStages] {};

@@ -724,10 +724,14 @@ extern "C" {
       RGC_CUDA(cudaEventCreate(&e));
     }
     {
-      cudaMemPool_t pool = nullptr;
-      RGC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+      cudaMemPoolProps props {};
+      props.allocType     = cudaMemAllocationTypePinned;
+      props.handleTypes   = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id   = device;
+      RGC_CUDA(cudaMemPoolCreate(&c.column_pool, &props));
       std::uint64_t keep = ~std::uint64_t(0); // freed columns stay cached for the next container
-      RGC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      RGC_CUDA(cudaMemPoolSetAttribute(c.column_pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
     c.launches    = 0;
     c.initialized = true;
@@ -738,9 +742,7 @@ extern "C" {
     RGC_REQUIRE_INIT();
     auto& c = ctx();
     RGC_CUDA(cudaStreamSynchronize(c.stream));
-    cudaMemPool_t pool = nullptr;
-    RGC_CUDA(cudaDeviceGetDefaultMemPool(&pool, c.device));
-    RGC_CUDA(cudaMemPoolTrimTo(pool, 0));
+    RGC_CUDA(cudaMemPoolTrimTo(c.column_pool, 0));
     return RGC_OK;
   }
 
@@ -751,12 +753,6 @@ extern "C" {
     }
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
-    {
-      cudaMemPool_t pool = nullptr;
-      if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) {
-        cudaMemPoolTrimTo(pool, 0);
-      }
-    }
     rgc_comm_destroy();
     io_release_lanes();
     pair_release_plans();
@@ -784,6 +780,10 @@ extern "C" {
         cudaEventDestroy(e);
         e = nullptr;
       }
+    }
+    if (c.column_pool) { // containers still alive keep their (now orphaned) columns until process exit
+      cudaMemPoolDestroy(c.column_pool);
+      c.column_pool = nullptr;
     }
     cudaStreamDestroy(c.stream);
     cudaStreamDestroy(c.copy_stream);
@@ -1018,8 +1018,8 @@ extern "C" {
     return RGC_OK;
   }
 
-  // Particle columns come from the device's stream-ordered memory pool (release threshold
-  // unlimited, set in rgc_init): a container that is dropped and re-created — what a script
+  // Particle columns come from the library's own stream-ordered memory pool (release threshold
+  // unlimited, created in rgc_init): a container that is dropped and re-created — what a script
   // does per species and step — gets its memory back without a device-wide cudaFree /
   // cudaMalloc round trip (tens of ms for GB-sized columns).  rgc_trim_memory() returns the
   // cached blocks to the device.
@@ -1051,7 +1051,8 @@ extern "C" {
   }
 
   static int alloc_column(float** col, std::size_t pitch) {
-    cudaError_t err = cudaMallocAsync(reinterpret_cast<void**>(col), pitch * sizeof(float), ctx().stream);
+    cudaError_t err = cudaMallocFromPoolAsync(reinterpret_cast<void**>(col), pitch * sizeof(float),
+                                              ctx().column_pool, ctx().stream);
     if (err != cudaSuccess) {
       cudaGetLastError();
       *col = nullptr;

@@ -190,6 +190,7 @@ extern "C" {
 
   int rgc_linspace_device(float start, float stop, size_t num, rgc_buf_t** out) {
     RGC_REQUIRE_INIT();
+    RGC_NVTX("Linspace");
     if (start >= stop) {
       return fail(RGC_ERR_INVALID, "Linspace start must be < stop");
     }
@@ -208,6 +209,7 @@ extern "C" {
 
   int rgc_logspace_device(float start, float stop, size_t num, rgc_buf_t** out) {
     RGC_REQUIRE_INIT();
+    RGC_NVTX("Logspace");
     if (start <= 0.0 or stop <= 0.0) {
       return fail(RGC_ERR_INVALID, "Logspace start and stop must be strictly positive");
     }
@@ -258,6 +260,7 @@ extern "C" {
 
   int rgc_buf_minmax(const rgc_buf_t* buf, float* min_out, float* max_out) {
     RGC_REQUIRE_INIT();
+    RGC_NVTX("XMinMax");
     if (!buf || rgc_buf_dtype(buf) != RGC_F32) {
       return fail(RGC_ERR_INVALID, "rgc_buf_minmax needs a float buffer");
     }
@@ -275,6 +278,7 @@ extern "C" {
   int rgc_tabulated_eval(int loggrid, const rgc_buf_t* tab_x, const rgc_buf_t* tab_y, float yfill,
                          const rgc_buf_t* x0, rgc_buf_t** out) {
     RGC_REQUIRE_INIT();
+    RGC_NVTX("InterpolateTabulatedFunction");
     if (!tab_x || !tab_y || !x0 || rgc_buf_dtype(tab_x) != RGC_F32 || rgc_buf_dtype(tab_y) != RGC_F32 ||
         rgc_buf_dtype(x0) != RGC_F32) {
       return fail(RGC_ERR_INVALID, "rgc_tabulated_eval needs float buffers");

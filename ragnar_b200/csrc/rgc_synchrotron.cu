@@ -700,6 +700,7 @@ extern "C" {
                                   const float* tab_y, size_t tab_n, float B0, float g_syn,
                                   float e_syn_at_g_syn, float* out_spec, double* out_spec64) {
     RGC_REQUIRE_INIT();
+    RGC_NVTX("SynchrotronSpectrum");
     // an unallocated container is an empty shard (the reference launches 0 x M threads over
     // empty Views): it still joins a multi-rank all-reduce, so no rank is left waiting
     const bool empty = (!p || !p->allocated) && nactive == 0;
@@ -727,6 +728,7 @@ extern "C" {
                             const float* tab_y, size_t tab_n, float B0, float g_syn,
                             float e_syn_at_g_syn, float* out_spec, double* out_spec64) {
     RGC_REQUIRE_INIT();
+    RGC_NVTX("ComputeEnergyDistribution + SynchrotronSpectrum");
     if (!p || !p->allocated) {
       return fail(RGC_ERR_INVALID, "Particles not allocated");
     }
@@ -786,6 +788,7 @@ extern "C" {
                                    float g_syn, float e_syn_at_g_syn, int mode, float* out_spec,
                                    double* out_spec64) {
     RGC_REQUIRE_INIT();
+    RGC_NVTX("SynchrotronSpectrum (FromDist)");
     if (nbins == 0 || nbatch == 0) {
       return RGC_OK;
     }
