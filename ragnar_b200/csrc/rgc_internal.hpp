@@ -65,7 +65,7 @@ namespace rgc {
 #define RGC_NVTX(name) ::rgc::NvtxRange rgc_nvtx_range__ { name }
 
   // ----------------------------------------------------------------- context
-  constexpr std::size_t kStageBytes = std::size_t(32) << 20; // per pinned stage
+  constexpr std::size_t kStageBytes = std::size_t(4) << 20; // per pinned stage of the small-copy ring
   constexpr int         kNumStages  = 4;
 
   struct Context {

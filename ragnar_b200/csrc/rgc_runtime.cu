@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <new>
@@ -103,11 +104,6 @@ namespace rgc {
     return attr.type == cudaMemoryTypeHost;
   }
 
-  // Worker threads that fill a pinned stage from a pageable source in parallel slices: one
-  // thread moves 4-10 GB/s, a PCIe 5 x16 link takes ~55 GB/s (measured on the bench box:
-  // 4 / 8 / 16 threads -> 31 / 32 / 51 GB/s end to end).  RGC_COPY_THREADS sets the width
-  // (default: the hardware threads divided by the ranks on the node); created on first
-  // use, joined in rgc_finalize.
   // memcpy into a pinned stage with non-temporal stores: the destination is read next by the
   // DMA engine, never by this core, so the read-for-ownership of a cached store (a third of
   // the host memory traffic of the copy) is skipped.  dst must be 32-byte aligned.
@@ -130,8 +126,8 @@ namespace rgc {
   }
 
   static void stage_copy(char* dst, const char* src, std::size_t bytes) {
-    // RGC_STAGE_NT=0 falls back to memcpy (measured on the bench box, tools/bench_fromarrays.py:
-    // 77-78 ms against 79-83 ms for the nine columns of 1e8 particles)
+    // RGC_STAGE_NT=0 falls back to memcpy (tools/mb_stage.cpp on the bench box, 16 threads:
+    // 83 GB/s with non-temporal stores, 67 with memcpy, 66 with rep movsb)
     static const bool avx2 = __builtin_cpu_supports("avx2") && [] {
       const char* e = std::getenv("RGC_STAGE_NT");
       return !(e && e[0] == '0');
@@ -143,11 +139,24 @@ namespace rgc {
     }
   }
 
+  // Staging pool for large pageable sources.  Every worker owns two pinned stages of
+  // kPoolChunk bytes and works on its own: claim the next chunk of the source (atomic
+  // counter), wait until its stage's previous DMA has finished, copy the chunk in with
+  // non-temporal stores, enqueue the DMA on the caller's stream, record the stage's event.
+  // No barrier between chunks — a worker's copy of chunk k+1 overlaps the DMA of its chunk k
+  // and everybody else's — one fork / join per copy_h2d call.
+  // Measured on the bench box (16 hardware threads, tools/mb_stage.cpp): the threads alone move
+  // 47 / 63 / 83 GB/s with 4 / 8 / 16 of them (the link takes 55); a first version that split
+  // every 32 MiB chunk over the threads behind a barrier reached 45 GB/s end to end.
+  // RGC_COPY_THREADS sets the width (default: the hardware threads divided by the ranks on the
+  // node, torchrun's LOCAL_WORLD_SIZE); created on first use, joined in rgc_finalize.
+  constexpr std::size_t kPoolChunk = std::size_t(8) << 20;
+
   class CopyPool {
   public:
-    explicit CopyPool(int n) {
+    explicit CopyPool(int n) : workers_(n) {
       for (int i = 0; i < n; ++i) {
-        workers_.emplace_back([this, i] { loop(i); });
+        workers_[i].th = std::thread([this, i] { loop(i); });
       }
     }
     ~CopyPool() {
@@ -156,24 +165,49 @@ namespace rgc {
         stop_ = true;
       }
       start_.notify_all();
-      for (auto& t : workers_) {
-        t.join();
+      for (auto& w : workers_) {
+        w.th.join();
+      }
+      for (auto& w : workers_) {
+        for (int s = 0; s < 2; ++s) {
+          if (w.stage[s]) {
+            cudaFreeHost(w.stage[s]);
+            cudaEventDestroy(w.free_ev[s]);
+          }
+        }
       }
     }
-    void copy(void* dst, const void* src, std::size_t bytes) {
+    // dst (device) <- src (pageable host), enqueued on `stream`; returns when every chunk has
+    // been staged and its DMA enqueued (the source may then be released; the stages are the
+    // pool's own).  Returns a cudaError_t as int (0 = ok).
+    int copy(void* dst, const void* src, std::size_t bytes, cudaStream_t stream, int device) {
       std::unique_lock<std::mutex> lk(m_);
       dst_     = static_cast<char*>(dst);
       src_     = static_cast<const char*>(src);
       bytes_   = bytes;
+      stream_  = stream;
+      device_  = device;
+      nchunks_ = (bytes + kPoolChunk - 1) / kPoolChunk;
+      next_.store(0);
+      err_.store(0);
       pending_ = (int)workers_.size();
       ++gen_;
       start_.notify_all();
       done_.wait(lk, [this] { return pending_ == 0; });
+      return err_.load();
     }
 
   private:
+    struct Worker {
+      std::thread th;
+      void*       stage[2] { nullptr, nullptr };
+      cudaEvent_t free_ev[2] { nullptr, nullptr };
+      int         next { 0 };
+    };
     void loop(int id) {
+      Worker&       w    = workers_[id];
       std::uint64_t seen = 0;
+      bool          ready = false;
       for (;;) {
         std::unique_lock<std::mutex> lk(m_);
         start_.wait(lk, [&] { return stop_ || gen_ != seen; });
@@ -183,13 +217,42 @@ namespace rgc {
         seen = gen_;
         char*             d = dst_;
         const char*       s = src_;
-        const std::size_t b = bytes_;
-        const std::size_t n = workers_.size();
+        const std::size_t b = bytes_, nch = nchunks_;
+        cudaStream_t      st = stream_;
+        const int         dev = device_;
         lk.unlock();
-        const std::size_t per = (((b + n - 1) / n) + 4095) & ~std::size_t(4095);
-        const std::size_t off = (std::size_t)id * per;
-        if (off < b) {
-          stage_copy(d + off, s + off, std::min(per, b - off));
+        cudaError_t e = cudaSuccess;
+        if (!ready) { // first job of this thread: its device and its two stages
+          e = cudaSetDevice(dev);
+          for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+            e = cudaHostAlloc(&w.stage[k], kPoolChunk, cudaHostAllocDefault);
+            if (e == cudaSuccess) {
+              e = cudaEventCreateWithFlags(&w.free_ev[k], cudaEventDisableTiming);
+            }
+          }
+          ready = e == cudaSuccess;
+        }
+        while (e == cudaSuccess) {
+          const std::size_t c = next_.fetch_add(1);
+          if (c >= nch) {
+            break;
+          }
+          const std::size_t off = c * kPoolChunk, len = std::min(kPoolChunk, b - off);
+          const int         k   = w.next;
+          e = cudaEventSynchronize(w.free_ev[k]); // never recorded yet: returns at once
+          if (e != cudaSuccess) {
+            break;
+          }
+          stage_copy(static_cast<char*>(w.stage[k]), s + off, len);
+          e = cudaMemcpyAsync(d + off, w.stage[k], len, cudaMemcpyHostToDevice, st);
+          if (e == cudaSuccess) {
+            e = cudaEventRecord(w.free_ev[k], st);
+          }
+          w.next ^= 1;
+        }
+        if (e != cudaSuccess) {
+          err_.store((int)e);
+          next_.store(nch); // the others stop claiming chunks
         }
         lk.lock();
         if (--pending_ == 0) {
@@ -197,7 +260,7 @@ namespace rgc {
         }
       }
     }
-    std::vector<std::thread> workers_;
+    std::vector<Worker>      workers_;
     std::mutex               m_;
     std::condition_variable  start_, done_;
     std::uint64_t            gen_ { 0 };
@@ -205,7 +268,11 @@ namespace rgc {
     bool                     stop_ { false };
     char*                    dst_ { nullptr };
     const char*              src_ { nullptr };
-    std::size_t              bytes_ { 0 };
+    std::size_t              bytes_ { 0 }, nchunks_ { 0 };
+    cudaStream_t             stream_ { nullptr };
+    int                      device_ { 0 };
+    std::atomic<std::size_t> next_ { 0 };
+    std::atomic<int>         err_ { 0 };
   };
 
   static CopyPool*  g_copy_pool = nullptr;
@@ -214,8 +281,6 @@ namespace rgc {
 
   static CopyPool* copy_pool() {
     if (!g_copy_pool) {
-      // one thread moves 4-10 GB/s; the default shares the hardware threads between the
-      // ranks of this node (torchrun's LOCAL_WORLD_SIZE), at most 32 per rank
       const int hw    = std::max(1, (int)std::thread::hardware_concurrency());
       const char* lws = std::getenv("LOCAL_WORLD_SIZE");
       int n = std::min(32, std::max(2, hw / std::max(1, lws ? std::atoi(lws) : 1)));
@@ -235,10 +300,10 @@ namespace rgc {
   }
 
   // Pinned sources go out as ONE async DMA (caller keeps them alive until the
-  // stream is synchronised); pageable sources are copied chunk-wise into a ring of
-  // pinned stages (large chunks by the worker pool above) so the CPU copy of chunk
-  // k+1 overlaps the DMA of chunk k.  The ring position persists between calls, so a
-  // run of small copies does not wait for the previous one's DMA.
+  // stream is synchronised); large pageable sources go through the staging pool above,
+  // small ones (< 4 MiB: bin edges, tables, plans) through a ring of pinned stages owned by
+  // the calling thread's context, whose position persists between calls so that a run of
+  // small copies does not wait for the previous one's DMA.
   int copy_h2d(void* dst, const void* src, std::size_t bytes, cudaStream_t stream) {
     if (bytes == 0) {
       return RGC_OK;
@@ -248,6 +313,15 @@ namespace rgc {
       return RGC_OK;
     }
     std::lock_guard<std::mutex> lk(g_stage_mutex);
+    if (bytes >= (std::size_t(4) << 20)) {
+      const int e = copy_pool()->copy(dst, src, bytes, stream, ctx().device);
+      if (e != 0) {
+        cudaGetLastError();
+        return fail(e == (int)cudaErrorMemoryAllocation ? RGC_ERR_OOM : RGC_ERR_CUDA,
+                    "staged host-to-device copy failed: %s", cudaGetErrorString((cudaError_t)e));
+      }
+      return RGC_OK;
+    }
     RGC_TRY(ensure_stages());
     auto&       c    = ctx();
     std::size_t done = 0;
@@ -255,11 +329,7 @@ namespace rgc {
       const int         s     = g_next_stage;
       const std::size_t chunk = bytes - done < kStageBytes ? bytes - done : kStageBytes;
       RGC_CUDA(cudaEventSynchronize(c.stage_free[s]));
-      if (chunk >= (std::size_t(4) << 20)) {
-        copy_pool()->copy(c.stage[s], static_cast<const char*>(src) + done, chunk);
-      } else {
-        std::memcpy(c.stage[s], static_cast<const char*>(src) + done, chunk);
-      }
+      std::memcpy(c.stage[s], static_cast<const char*>(src) + done, chunk);
       RGC_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + done, c.stage[s], chunk,
                                cudaMemcpyHostToDevice, stream));
       RGC_CUDA(cudaEventRecord(c.stage_free[s], stream));
