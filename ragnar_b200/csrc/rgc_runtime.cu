@@ -24,6 +24,7 @@
 #include <condition_variable>
 #include <mutex>
 #include <new>
+#include <string>
 #include <thread>
 
 namespace rgc {
@@ -126,11 +127,12 @@ namespace rgc {
   }
 
   static void stage_copy(char* dst, const char* src, std::size_t bytes) {
-    // RGC_STAGE_NT=0 falls back to memcpy (tools/mb_stage.cpp on the bench box, 16 threads:
-    // 83 GB/s with non-temporal stores, 67 with memcpy, 66 with rep movsb)
+    // RGC_STAGE_NT=1 selects non-temporal stores: faster in isolation (tools/mb_stage.cpp, 16
+    // threads: 83 GB/s against 67 with memcpy) but they push every stage out to DRAM, where the
+    // DMA engine then has to fetch it; off by default (see StageGeometry below)
     static const bool avx2 = __builtin_cpu_supports("avx2") && [] {
       const char* e = std::getenv("RGC_STAGE_NT");
-      return !(e && e[0] == '0');
+      return e && e[0] == '1';
     }();
     if (avx2 && (reinterpret_cast<std::uintptr_t>(dst) & 31u) == 0 && bytes >= 4096) {
       stream_copy_avx2(dst, src, bytes);
@@ -139,19 +141,85 @@ namespace rgc {
     }
   }
 
-  // Staging pool for large pageable sources.  Every worker owns two pinned stages of
-  // kPoolChunk bytes and works on its own: claim the next chunk of the source (atomic
-  // counter), wait until its stage's previous DMA has finished, copy the chunk in with
-  // non-temporal stores, enqueue the DMA on the caller's stream, record the stage's event.
-  // No barrier between chunks — a worker's copy of chunk k+1 overlaps the DMA of its chunk k
-  // and everybody else's — one fork / join per copy_h2d call.
-  // Measured on the bench box (16 hardware threads, tools/mb_stage.cpp): the threads alone move
-  // 47 / 63 / 83 GB/s with 4 / 8 / 16 of them (the link takes 55); a first version that split
-  // every 32 MiB chunk over the threads behind a barrier reached 45 GB/s end to end.
-  // RGC_COPY_THREADS sets the width (default: the hardware threads divided by the ranks on the
-  // node, torchrun's LOCAL_WORLD_SIZE); created on first use, joined in rgc_finalize.
-  constexpr std::size_t kPoolChunk = std::size_t(8) << 20;
+  // Staging pool for large pageable sources.  Every worker owns two pinned stages and works
+  // on its own: claim the next chunk of the source (atomic counter), wait until its stage's
+  // previous DMA has finished, copy the chunk in, enqueue the DMA on the caller's stream,
+  // record the stage's event.  No barrier between chunks — a worker's copy of chunk k+1
+  // overlaps the DMA of its chunk k and everybody else's — one fork / join per copy_h2d call.
+  // Created on first use, joined in rgc_finalize.
+  // Geometry of the pool: the stages must stay in the last-level cache.  A chunk is written by
+  // a core (plain stores) and read once by the DMA engine; while all stages together fit the
+  // L3, that read is served from the cache and host DRAM only sees the source being read —
+  // one pass instead of three.  Measured (tools/bench_fromarrays.py, bench.py e2e): on one
+  // bench box 8 MiB stages written with non-temporal stores gave 71 ms for 3.6 GB, on the next
+  // one 110 ms, where 8 workers x 2 x 2 MiB of plain stores gave 73 ms; with two ranks sharing
+  // a host 122 ms against 86 ms (12 workers x 2 x 1 MiB each).  So: budget = 0.6 x L3 / ranks
+  // on the node, at most 8 workers, chunks of budget / (2 x workers) within [1, 8] MiB (below
+  // 1 MiB the per-copy cost of the DMA engine shows), fewer workers when even that does not
+  // fit.  RGC_COPY_THREADS / RGC_STAGE_CHUNK_KB override; RGC_STAGE_NT=1 selects non-temporal stores.
+  struct StageGeometry {
+    int         workers;
+    std::size_t chunk;
+  };
 
+  static std::size_t l3_bytes() {
+    std::size_t total = 0;
+    std::vector<std::string> seen;
+    for (int cpu = 0; cpu < 1024; ++cpu) {
+      const std::string base = "/sys/devices/system/cpu/cpu" + std::to_string(cpu) + "/cache/index3/";
+      FILE* f = std::fopen((base + "shared_cpu_list").c_str(), "r");
+      if (!f) {
+        if (cpu == 0) {
+          break;
+        }
+        continue;
+      }
+      char who[256] = { 0 };
+      const bool got = std::fgets(who, sizeof(who), f) != nullptr;
+      std::fclose(f);
+      if (!got || std::find(seen.begin(), seen.end(), std::string(who)) != seen.end()) {
+        continue; // this L3 instance is counted already
+      }
+      seen.emplace_back(who);
+      if (FILE* g = std::fopen((base + "size").c_str(), "r")) {
+        unsigned long v = 0;
+        char          unit = 'K';
+        if (std::fscanf(g, "%lu%c", &v, &unit) >= 1) {
+          total += (std::size_t)v << (unit == 'M' ? 20 : (unit == 'G' ? 30 : 10));
+        }
+        std::fclose(g);
+      }
+    }
+    return total ? total : (std::size_t(32) << 20);
+  }
+
+  static const StageGeometry& stage_geometry() {
+    static const StageGeometry g = [] {
+      const int   hw   = std::max(1, (int)std::thread::hardware_concurrency());
+      const char* lws  = std::getenv("LOCAL_WORLD_SIZE");
+      const int   rpn  = std::max(1, lws ? std::atoi(lws) : 1); // ranks on this node (torchrun)
+      const std::size_t MiB = std::size_t(1) << 20;
+      const std::size_t budget = std::max(4 * MiB, (std::size_t)(0.6 * (double)l3_bytes()) / rpn);
+      StageGeometry     sg;
+      sg.workers = std::min(8, std::max(2, hw / rpn));
+      if (const char* e = std::getenv("RGC_COPY_THREADS")) {
+        sg.workers = std::max(1, std::min(std::atoi(e), 64));
+      }
+      sg.chunk = std::min(8 * MiB, std::max(MiB, budget / (2 * (std::size_t)sg.workers) / (256 << 10) * (256 << 10)));
+      if (!std::getenv("RGC_COPY_THREADS") && 2 * (std::size_t)sg.workers * sg.chunk > budget) {
+        sg.workers = (int)std::max<std::size_t>(2, budget / (2 * sg.chunk));
+      }
+      if (const char* e = std::getenv("RGC_STAGE_CHUNK_KB")) {
+        const long kb = std::atol(e);
+        if (kb >= 64 && kb <= (1 << 16)) {
+          sg.chunk = (std::size_t)kb << 10;
+        }
+      }
+      return sg;
+    }();
+    return g;
+  }
+#define kPoolChunk (stage_geometry().chunk)
   class CopyPool {
   public:
     explicit CopyPool(int n) : workers_(n) {
@@ -281,14 +349,7 @@ namespace rgc {
 
   static CopyPool* copy_pool() {
     if (!g_copy_pool) {
-      const int hw    = std::max(1, (int)std::thread::hardware_concurrency());
-      const char* lws = std::getenv("LOCAL_WORLD_SIZE");
-      int n = std::min(32, std::max(2, hw / std::max(1, lws ? std::atoi(lws) : 1)));
-      if (const char* s = std::getenv("RGC_COPY_THREADS")) {
-        n = std::atoi(s);
-      }
-      n = std::max(1, std::min(n, 64));
-      g_copy_pool = new CopyPool(n);
+      g_copy_pool = new CopyPool(stage_geometry().workers);
     }
     return g_copy_pool;
   }
