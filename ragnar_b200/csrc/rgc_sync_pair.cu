@@ -71,15 +71,18 @@ namespace rgc {
 
   constexpr int kPThreads    = 256;
   constexpr int kPWarps      = kPThreads / 32;
-  constexpr int kPMaxGPW     = 8;
-  constexpr int kPMaxBins    = 8 * (kPMaxGPW * 32 - 2); // 2032 per launch
+  constexpr int kPMaxGPW     = 8;    // lane groups a warp evaluates at once (one chunk)
+  constexpr int kSubDiv      = 8;    // a table cell is cut into eighths of the fraction fc ...
+  constexpr int kSub         = kSubDiv + 1; // ... shifted by the plan's phase: 9 sub-buckets, s = floor(8 fc + phi)
+  constexpr int kMomStride   = 2 * kSub + 2; // floats per piece in piece_mom (16-byte multiple)
+  constexpr int kPMaxBins    = 2032; // per launch
+  constexpr int kPMaxGroups  = 96;   // lane groups per launch (bins by sub-bucket + moment lanes)
   constexpr int kPMaxBuckets = 1024;
   constexpr unsigned kInvalidKey = 0xffffu;
   constexpr int kPTile       = 4096; // particles per tile of the prologue / sort kernels
   constexpr int kPSteps      = kPTile / kPThreads;
-  constexpr int kPieceLen    = 1024; // sorted entries per work unit of the pair kernel
-  constexpr int kStageLen    = 64;   // sorted entries per TMA stage (512 B)
-  constexpr int kStages      = 4;    // ring depth per warp
+  constexpr int kPieceLen    = 512;  // sorted entries per work unit of the pair kernel
+  constexpr int kPieceEnt    = kPieceLen / 32; // entries per lane in the piece's sub-sort
 
   // fp64 constants of the prologue, read as constant-bank operands (an immediate double
   // whose low word is not zero costs two UMOVs per use otherwise)
@@ -95,9 +98,13 @@ namespace rgc {
     const float* b[3];
     std::size_t  nprtl;
     const int2*   slot_i;  // per slot {Aoff, -}: cell q = max(Aoff + bucket, 0); spare slots Aoff << 0
-    const float2* slot_f;  // per slot {fa0, -}:  fa' = (fa0 - h_q) * sign_q
+    const float2* slot_f;  // per slot {fa0, -}
     const float4* coef_dh; // per padded cell {hinge coefficient, hinge position, sign, 0}
-    int n_pad, nb, nbp, ncols;
+    const int4*   chunks;  // {first lane group, groups (<= kPMaxGPW), carries the moment lanes, -}
+    const unsigned char* na_tab; // [bucket][chunk] leading groups of the chunk that are on the table
+    const unsigned*      extmask; // [bucket] bit s: sub-bucket s also sees run s - 1; bit kSub + s: run s + 1
+    int chunk_first[kSub + 1]; // chunks of sub-bucket s: [chunk_first[s], chunk_first[s + 1])
+    int n_pad, nb, nbp, nchunks;
     int kmin;              // bucket = floor(c) - kmin
     double kmin_d;
     double inv_B0;           // 1 / B0
@@ -112,34 +119,43 @@ namespace rgc {
     int*        counts; // [nbp][rows]: per-row bucket counts, then offsets inside the bucket
     int*        tot;    // [nbp] valid particles per bucket
     float2*     sorted; // (fc, w) in global bucket order, every bucket padded to an even length
-    float2*     piece_mom; // [piece] {S0, S1} of the piece (float sums of <= kPieceLen terms)
+    float*      piece_mom; // [piece][kMomStride]: {S0, S1} of the piece's kSub sub-bucket runs (float sums)
+    float       sub_phi;   // phase of the sub-bucket boundaries: s = floor(kSubDiv fc + sub_phi)
     int*        poison;    // != 0: a particle's chiR overflows float (see pair_prologue)
     unsigned long long* lane_evals; // hinge evaluations the pair kernel issued (roofline accounting)
-    unsigned force_groups;          // lane groups evaluated even when all their lanes sit on zero cells
-    double*     partials;  // [cta][nslots] hinge sums
+    unsigned force_groups;          // != 0: lane groups are evaluated even when all their lanes sit on zero cells
+    double*     partials;  // [warp of the grid][nslots] hinge sums (RED.ADD.F64 targets, zeroed per pass)
+    double*     cta_partials; // [cta][nslots]: the CTA's warp rows summed in warp order
     int         nslots;
     // shared-memory layout of the pair kernel (byte offsets, computed once on the host)
-    int o_coef, o_bstart, o_pstart, o_tmp, o_ring, o_mbar, o_red;
+    int o_coef, o_bstart, o_pstart, o_tmp, o_slot, o_chunk, o_warp, warp_stride;
   };
 
   __host__ __device__ inline std::size_t pair_align16(std::size_t x) { return (x + 15) & ~std::size_t(15); }
 
   struct PairSmem {
-    std::size_t coef, bstart, pstart, tmp, ring, mbar, red, total;
+    std::size_t coef, bstart, pstart, tmp, slot, chunk, warp, warp_stride, total;
   };
+  // per-warp region of the pair kernel: the piece sorted by sub-bucket (every run padded to a
+  // multiple of 8 entries), the per-lane cursors of the sort, the run table
+  constexpr std::size_t kPWarpB      = 0;
+  constexpr std::size_t kPWarpCur    = kPWarpB + (std::size_t)(kPieceLen + 8 * kSub) * sizeof(float2);
+  constexpr std::size_t kPWarpRun    = kPWarpCur + (std::size_t)kSub * 32 * sizeof(int);
+  constexpr std::size_t kPWarpStride = (kPWarpRun + (std::size_t)kSub * sizeof(int2) + 127) & ~std::size_t(127);
 
-  __host__ __device__ inline PairSmem pair_smem_layout(int n_pad, int nbp, int gpw) {
+  __host__ __device__ inline PairSmem pair_smem_layout(int n_pad, int nbp, int nslots, int nchunks) {
     PairSmem L;
     std::size_t o = 0;
     L.coef = o;    o = pair_align16(o + (std::size_t)n_pad * sizeof(float4));
     L.bstart = o;  o = pair_align16(o + (std::size_t)(nbp + 2) * sizeof(int));
     L.pstart = o;  o = pair_align16(o + (std::size_t)(nbp + 2) * sizeof(int));
     L.tmp = o;     o = pair_align16(o + (std::size_t)(2 * kPWarps) * sizeof(int));
+    L.slot = o;    o = pair_align16(o + (std::size_t)nslots * sizeof(int2));
+    L.chunk = o;   o = pair_align16(o + (std::size_t)nchunks * sizeof(int4));
     o = (o + 127) & ~std::size_t(127);
-    L.ring = o;    o = pair_align16(o + (std::size_t)kPWarps * kStages * kStageLen * sizeof(float2));
-    L.mbar = o;    o = pair_align16(o + (std::size_t)kPWarps * kStages * 8);
-    L.red = o;     o = pair_align16(o + (std::size_t)kPWarps * gpw * 32 * sizeof(double));
-    L.total = o;
+    L.warp        = o;
+    L.warp_stride = kPWarpStride;
+    L.total       = o + (std::size_t)kPWarps * kPWarpStride;
     return L;
   }
 
@@ -750,58 +766,67 @@ namespace rgc {
     }
   }
 
-  // ---- kernel 4: the pair loop over the globally bucket-sorted (fc, w)
-  template <int GPW>
-  __global__ void __launch_bounds__(kPThreads, 2)
+  // ---- kernel 4: the pair loop over the globally bucket-sorted (fc, w).
+  //
+  // A piece (<= kPieceLen sorted entries of one bucket) belongs to one warp.  The hinge
+  // r = max(0, fc + fa') of bin j is identically 0 for every particle with fc <= -fa' and
+  // linear in fc for every particle above, so only particles whose fc lies in the same
+  // eighth of the cell as the bin's threshold -fa' need per-pair work; the others enter
+  // through the moments (S0, S1) of their sub-bucket, which the first two lanes of every
+  // sub-bucket's first lane group deliver for free (pair_final_kernel adds that part).
+  // The warp therefore
+  //   1. lands the piece in shared memory with one TMA bulk copy (the next piece's copy is
+  //      issued as soon as the entries sit in registers),
+  //   2. sorts it by sub-bucket s = floor(8 fc) into per-lane cursor order (counting sort,
+  //      every lane owns 16 entries and its own cursor column: no atomics, order fixed by
+  //      (lane, entry)), every run padded to an even length,
+  //   3. streams run s through the lane groups that hold the bins whose threshold lies in
+  //      sub-bucket s (plus, rarely, the neighbouring sub-bucket's groups when a threshold
+  //      sits within the table nodes' wiggle of a boundary): FADD.SAT + FFMA per
+  //      evaluation, fed by broadcast LDS.128,
+  //   4. adds ds_q * sum (fp64) into its private row of the partial sums with RED.ADD.F64
+  //      (one row per warp of the grid: the order of additions is the warp's own).
+  // A cell pair next to the table's zero tail (sign < 0) needs sum w max(0, 1 - u): its
+  // lanes run the same two instructions on sat(fc + fa0) and the run's S0 lane gives
+  // S0 - sum w sat(u), which is exactly 0 when every particle of the run is beyond the
+  // tail (both lanes then execute the identical float sequence).
+  template <int MAXNA>
+  __global__ void __launch_bounds__(kPThreads, MAXNA <= 2 ? 3 : 2)
     sync_pair_kernel(const __grid_constant__ PairParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4*             coef   = reinterpret_cast<float4*>(smem_raw + P.o_coef);
-    int*                bstart = reinterpret_cast<int*>(smem_raw + P.o_bstart);
-    int*                pstart = reinterpret_cast<int*>(smem_raw + P.o_pstart);
-    int*                tmp    = reinterpret_cast<int*>(smem_raw + P.o_tmp);
-    double*             red    = reinterpret_cast<double*>(smem_raw + P.o_red);
+    float4* coef     = reinterpret_cast<float4*>(smem_raw + P.o_coef);
+    int*    bstart   = reinterpret_cast<int*>(smem_raw + P.o_bstart);
+    int*    pstart   = reinterpret_cast<int*>(smem_raw + P.o_pstart);
+    int*    tmp      = reinterpret_cast<int*>(smem_raw + P.o_tmp);
+    int2*   slot_tab = reinterpret_cast<int2*>(smem_raw + P.o_slot);
+    int4*   chunks   = reinterpret_cast<int4*>(smem_raw + P.o_chunk);
 
     const int tid  = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int col  = warp % P.ncols;
     const int nb   = P.nb;
-    float4*             ring = reinterpret_cast<float4*>(smem_raw + P.o_ring) +
-                   warp * (kStages * kStageLen / 2);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + P.o_mbar) +
-                               warp * kStages;
-    if (lane == 0) {
-#pragma unroll
-      for (int s = 0; s < kStages; ++s) {
-        mbar_init(&bars[s], 1);
-      }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    unsigned char* wbase  = smem_raw + P.o_warp + (std::size_t)warp * P.warp_stride;
+    float2*        B      = reinterpret_cast<float2*>(wbase + kPWarpB);
+    int*           cur    = reinterpret_cast<int*>(wbase + kPWarpCur);
+    int2*          runtab = reinterpret_cast<int2*>(wbase + kPWarpRun);
     for (int i = tid; i < P.n_pad; i += kPThreads) {
       coef[i] = P.coef_dh[i];
     }
+    for (int i = tid; i < P.nslots; i += kPThreads) {
+      slot_tab[i] = make_int2(P.slot_i[i].x, __float_as_int(P.slot_f[i].x));
+    }
+    for (int i = tid; i < P.nchunks; i += kPThreads) {
+      chunks[i] = P.chunks[i];
+    }
     block_scan_buckets(P.tot, nb, bstart, pstart, tmp); // ends with __syncthreads()
 
-    int    aoff[GPW];
-    float  fa0[GPW];
-    double accd[GPW];
-#pragma unroll
-    for (int g = 0; g < GPW; ++g) {
-      const int    slot = (col * GPW + g) * 32 + lane;
-      const int2   si   = P.slot_i[slot];
-      const float2 sf   = P.slot_f[slot];
-      aoff[g] = si.x;
-      fa0[g]  = sf.x;
-      accd[g] = 0.0;
-    }
-
     const int npieces = pstart[nb];
-    const int wstride = (gridDim.x * kPWarps) / P.ncols;
-    unsigned  tstage  = 0; // stages issued so far by this warp (ring slot and parity)
-    unsigned long long lane_evals = 0; // hinge evaluations issued by this warp (32 per group and entry)
-
-    for (int piece = (blockIdx.x * kPWarps + warp) / P.ncols; piece < npieces; piece += wstride) {
-      // bucket of the piece: first b with pstart[b + 1] > piece
+    const int wstride = gridDim.x * kPWarps;
+    const int gwarp   = blockIdx.x * kPWarps + warp;
+    double*   prow    = P.partials + (std::size_t)gwarp * P.nslots;
+    unsigned long long lane_evals = 0; // hinge evaluations issued by this warp
+    // bucket and sorted range of a piece: first b with pstart[b + 1] > piece
+    auto locate = [&](int piece, int& b, int& beg, int& end) {
       int lo = 0, hi = nb - 1;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -811,177 +836,230 @@ namespace rgc {
           hi = mid;
         }
       }
-      const int b    = lo;
-      const int beg  = bstart[b] + (piece - pstart[b]) * kPieceLen;
-      const int end  = min(beg + kPieceLen, bstart[b + 1]);
-      const int nst  = (end - beg + kStageLen - 1) / kStageLen;
+      b   = lo;
+      beg = bstart[lo] + (piece - pstart[lo]) * kPieceLen;
+      end = min(beg + kPieceLen, bstart[lo + 1]);
+    };
+    int piece = gwarp, b = 0, beg = 0, end = 0;
+    if (piece < npieces) {
+      locate(piece, b, beg, end);
+    }
+    while (piece < npieces) {
+      const int n = end - beg; // even, <= kPieceLen
+      // ---- 1. the piece: 16 coalesced 8-byte loads per lane, all in flight at once (entries
+      // beyond a short piece become zero-weight pads); the bucket's chunk table rides along
+      float2        ent[kPieceEnt];
       const float2* src = P.sorted + beg;
-      // coefficients of this warp's lanes for the bucket, and the number NA of leading
-      // lane groups that can receive anything: a group whose 32 lanes all sit on zero cell
-      // pairs (x0 = e_syn / e_peak beyond the table's zero tail; bins ascend, so these are
-      // the trailing groups) has ds = 0 in every lane and is not evaluated at all — the
-      // reference's own `x0 >= xmax -> yfill` early-out, at group granularity.  Group 0
-      // carries the moment lanes of column 0 and always runs there.
-      float fap[GPW], sgn[GPW], ds[GPW], s2[GPW], s2p[GPW];
-      unsigned active = 0;
 #pragma unroll
-      for (int g = 0; g < GPW; ++g) {
-        const float4 dh = coef[max(aoff[g] + b, 0)];
-        ds[g]  = dh.x;
-        sgn[g] = dh.z;
-        fap[g] = (fa0[g] - dh.y) * dh.z;
-        s2[g]  = 0.0f;
-        s2p[g] = 0.0f;
-        active |= __any_sync(0xffffffffu, dh.x != 0.0f) ? (1u << g) : 0u;
+      for (int st = 0; st < kPieceEnt; ++st) {
+        const int e = st * 32 + lane;
+        ent[st]     = e < n ? __ldcs(src + e) : make_float2(0.0f, 0.0f);
       }
-      if (col == 0) {
-        active |= 1u;
+      const unsigned       em     = P.extmask[b];
+      const unsigned char* na_row = P.na_tab + (std::size_t)b * P.nchunks;
+      unsigned             na_reg[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        na_reg[q] = q * 32 + lane < P.nchunks ? (unsigned)na_row[q * 32 + lane] : 0u;
       }
-      active |= P.force_groups; // test knob RGC_PAIR_NO_SKIP: evaluate every group
-      if (active == 0u) {
-        continue; // nothing of this column's bins is on the table for this bucket
+      // ---- 2. counting sort by sub-bucket; a lane's entries and cursors are its own
+      // (5-bit per-lane counters of the 9 sub-buckets packed into one 64-bit register)
+      unsigned long long cnt = 0ull;
+#pragma unroll
+      for (int st = 0; st < kPieceEnt; ++st) {
+        const int s = min(kSub - 1, (int)fmaf(ent[st].x, (float)kSubDiv, P.sub_phi));
+        cnt += 1ull << (5 * s);
       }
-      const int na = 32 - __clz(active);
-      lane_evals += (unsigned long long)(end - beg) * (unsigned)(na * 32);
-      auto issue = [&](int s) { // stage s of this piece -> ring slot (tstage + s) % kStages
-        const unsigned slot  = (tstage + (unsigned)s) % kStages;
-        const int      cnt   = min(kStageLen, end - beg - s * kStageLen);
-        const unsigned bytes = (unsigned)cnt * sizeof(float2);
-        mbar_expect_tx(&bars[slot], bytes);
-        bulk_g2s(ring + slot * (kStageLen / 2), src + s * kStageLen, bytes, &bars[slot]);
-      };
-      if (lane == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int s = 0; s < min(nst, kStages); ++s) {
-          issue(s);
+      {
+        int run = 0;
+#pragma unroll
+        for (int k = 0; k < kSub; ++k) {
+          const int c    = (int)((cnt >> (5 * k)) & 31ull);
+          int       incl = c;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) {
+              incl += t;
+            }
+          }
+          const int tot      = __shfl_sync(0xffffffffu, incl, 31);
+          const int padded   = (tot + 7) & ~7; // whole groups of 4 float4
+          cur[k * 32 + lane] = run + incl - c;
+          if (lane == k) {
+            runtab[k] = make_int2(run, padded);
+          }
+          if (lane < padded - tot) {
+            B[run + tot + lane] = make_float2(0.0f, 0.0f); // zero-weight pad
+          }
+          run += padded;
         }
       }
-      // s2: float sums of up to 256 entries, folded into the piece's sums s2p: short float
-      // chains bound the rounding drift of long runs of identical addends (a mono-energetic
-      // population, where the drift is one-sided and the same in every piece) to ~1e-5;
-      // folding every 64 entries would give 3e-6 for 5 % of this kernel's time
-      auto run_piece = [&](auto na_tag) {
-        constexpr int NA = decltype(na_tag)::value;
-#define RGC_PAIR_ONE(FC, W)                                                         \
-  {                                                                                 \
-    float r[NA];                                                                    \
-    _Pragma("unroll") for (int g = 0; g < NA; ++g) { r[g] = __saturatef(fmaf((FC), sgn[g], fap[g])); } \
-    _Pragma("unroll") for (int g = 0; g < NA; ++g) { s2[g] = fmaf((W), r[g], s2[g]); }     \
-  }
-#define RGC_PAIR_BODY(Q) RGC_PAIR_ONE((Q).x, (Q).y) RGC_PAIR_ONE((Q).z, (Q).w)
-        for (int s = 0; s < nst; ++s) {
-          const unsigned t    = tstage + (unsigned)s;
-          const unsigned slot = t % kStages;
-          mbar_wait(&bars[slot], (t / kStages) & 1u);
-          const float4* buf = ring + slot * (kStageLen / 2);
-          const int     nq  = min(kStageLen, end - beg - s * kStageLen) >> 1; // float4 = 2 entries
-          if (nq == kStageLen / 2) {
-            // Two particles per broadcast LDS.128; the loads of the next two float4 are in
-            // flight while the current two are consumed (ping-pong registers).  Per particle
-            // all hinges first, then all accumulates, so no FFMA waits on the FFMA.SAT
-            // just before it.
-            float4 q0 = buf[0];
-            float4 q1 = buf[1];
-#pragma unroll 1
-            for (int p = 0; p < kStageLen / 2 - 4; p += 4) {
-              const float4 a0 = buf[p + 2];
-              const float4 a1 = buf[p + 3];
-              RGC_PAIR_BODY(q0)
-              RGC_PAIR_BODY(q1)
-              q0 = buf[p + 4];
-              q1 = buf[p + 5];
-              RGC_PAIR_BODY(a0)
-              RGC_PAIR_BODY(a1)
-            }
-            {
-              const float4 a0 = buf[kStageLen / 2 - 2];
-              const float4 a1 = buf[kStageLen / 2 - 1];
-              RGC_PAIR_BODY(q0)
-              RGC_PAIR_BODY(q1)
-              RGC_PAIR_BODY(a0)
-              RGC_PAIR_BODY(a1)
-            }
-          } else {
-            for (int p = 0; p < nq; ++p) {
-              const float4 q = buf[p];
-              RGC_PAIR_BODY(q)
-            }
-          }
-          __syncwarp();
-          if (lane == 0 && s + kStages < nst) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(s + kStages);
-          }
-          if ((s & 3) == 3 || s + 1 == nst) { // every 256 entries
+      {
+        unsigned long long seen = 0ull;
 #pragma unroll
-            for (int g = 0; g < NA; ++g) {
-              s2p[g] += s2[g];
-              s2[g] = 0.0f;
-            }
-          }
+        for (int st = 0; st < kPieceEnt; ++st) {
+          const int s    = min(kSub - 1, (int)fmaf(ent[st].x, (float)kSubDiv, P.sub_phi));
+          const int rank = (int)((seen >> (5 * s)) & 31ull);
+          seen += 1ull << (5 * s);
+          B[cur[s * 32 + lane] + rank] = ent[st];
+        }
+      }
+      __syncwarp();
+      // the next piece of this warp
+      const int npiece = piece + wstride;
+      int       nbk = 0, nbeg = 0, nend = 0;
+      if (npiece < npieces) {
+        locate(npiece, nbk, nbeg, nend);
+      }
+      // ---- 3. the runs
+      float* pm    = P.piece_mom + (std::size_t)piece * kMomStride;
+      float  s0run = 0.0f;
+      // one chunk (<= kPMaxGPW lane groups, the first NA of them on the table for this bucket)
+      // over the run [rb, rb + n4): r = sat(fc + fa'), acc += w r.  Two accumulator chains per
+      // group, the same for every NA: the zero-tail lanes rely on identical float sequences.
+      auto run_chunk = [&](auto na_tag, const int4 ch, const bool own, const int r,
+                           const float4* __restrict__ rb, const int n4) {
+        constexpr int NA = decltype(na_tag)::value;
+        float    fap[NA], ds[NA], acc[2][NA];
+        unsigned rtype = 0;
+#pragma unroll
+        for (int g = 0; g < NA; ++g) {
+          const int2   sl    = slot_tab[(ch.x + g) * 32 + lane];
+          const float  fa0   = __int_as_float(sl.y);
+          const float4 dh    = coef[max(sl.x + b, 0)];
+          const bool   spare = sl.x < 0;              // moment lanes and unused lanes
+          const bool   tail  = !spare && dh.z < 0.0f; // cell pair next to the zero tail
+          fap[g]    = spare ? fa0 - 1.0f : (tail ? fa0 : fa0 - dh.y);
+          ds[g]     = spare ? 0.0f : dh.x;
+          rtype |= tail ? (1u << g) : 0u;
+          acc[0][g] = 0.0f;
+          acc[1][g] = 0.0f;
+        }
+#define RGC_PAIR_ONE(FC, W, SET)                                                              \
+  {                                                                                           \
+    float rr[NA];                                                                             \
+    _Pragma("unroll") for (int g = 0; g < NA; ++g) { rr[g] = __saturatef((FC) + fap[g]); }    \
+    _Pragma("unroll") for (int g = 0; g < NA; ++g) { acc[SET][g] = fmaf((W), rr[g], acc[SET][g]); } \
+  }
+#define RGC_PAIR_BODY(Q) RGC_PAIR_ONE((Q).x, (Q).y, 0) RGC_PAIR_ONE((Q).z, (Q).w, 1)
+        // runs are padded to whole groups of 4 float4 (8 entries); the loads of the next two
+        // float4 are in flight while the current two are consumed (ping-pong registers)
+        float4 q0 = rb[0], q1 = rb[1];
+#pragma unroll 1
+        for (int p = 0; p < n4 - 4; p += 4) {
+          const float4 a0 = rb[p + 2], a1 = rb[p + 3];
+          RGC_PAIR_BODY(q0)
+          RGC_PAIR_BODY(q1)
+          q0 = rb[p + 4];
+          q1 = rb[p + 5];
+          RGC_PAIR_BODY(a0)
+          RGC_PAIR_BODY(a1)
+        }
+        {
+          const float4 a0 = rb[n4 - 2], a1 = rb[n4 - 1];
+          RGC_PAIR_BODY(q0)
+          RGC_PAIR_BODY(q1)
+          RGC_PAIR_BODY(a0)
+          RGC_PAIR_BODY(a1)
         }
 #undef RGC_PAIR_BODY
 #undef RGC_PAIR_ONE
-      };
-      switch (na) {
-#define RGC_NA_CASE(N)                                            \
-  case N:                                                         \
-    if constexpr (N <= GPW) {                                     \
-      run_piece(std::integral_constant<int, N> {});               \
-    }                                                             \
-    break;
-        RGC_NA_CASE(1)
-        RGC_NA_CASE(2)
-        RGC_NA_CASE(3)
-        RGC_NA_CASE(4)
-        RGC_NA_CASE(5)
-        RGC_NA_CASE(6)
-        RGC_NA_CASE(7)
-        RGC_NA_CASE(8)
-#undef RGC_NA_CASE
-      }
-      tstage += (unsigned)nst;
+        const float m0 = acc[0][0] + acc[1][0];
+        if (own && ch.z != 0) {
+          s0run = __shfl_sync(0xffffffffu, m0, 0);
+          if (lane < 2) {
+            pm[r * 2 + lane] = m0; // lanes 0 / 1 of group 0: S0 / S1 of the run
+          }
+        }
 #pragma unroll
-      for (int g = 0; g < GPW; ++g) {
-        accd[g] = fma((double)ds[g], (double)s2p[g], accd[g]);
+        for (int g = 0; g < NA; ++g) {
+          if (ds[g] != 0.0f) {
+            const float s2 = acc[0][g] + acc[1][g];
+            const float v  = ((rtype >> g) & 1u) ? s0run - s2 : s2;
+            atomicAdd(&prow[(ch.x + g) * 32 + lane], (double)ds[g] * (double)v);
+          }
+        }
+      };
+      auto do_chunks = [&](const int sub, const bool own, const int r, const float4* rb, const int n4,
+                           const int len) {
+        for (int c = P.chunk_first[sub]; c < P.chunk_first[sub + 1]; ++c) {
+          const int4 ch = chunks[c];
+          const unsigned nav = c < 32 ? na_reg[0] : (c < 64 ? na_reg[1] : na_reg[2]);
+          const int      na  = P.force_groups != 0u ? ch.y : (int)__shfl_sync(0xffffffffu, nav, c & 31);
+          if (na == 0) {
+            continue; // none of these bins is on the table for this bucket
+          }
+          lane_evals += (unsigned long long)len * (unsigned)(na * 32);
+          switch (na) {
+#define RGC_NA_CASE(N)                                                        \
+  case N:                                                                     \
+    if constexpr (N <= MAXNA) {                                               \
+      run_chunk(std::integral_constant<int, N> {}, ch, own, r, rb, n4);       \
+    }                                                                         \
+    break;
+            RGC_NA_CASE(1)
+            RGC_NA_CASE(2)
+            RGC_NA_CASE(3)
+            RGC_NA_CASE(4)
+            RGC_NA_CASE(5)
+            RGC_NA_CASE(6)
+            RGC_NA_CASE(7)
+            RGC_NA_CASE(8)
+#undef RGC_NA_CASE
+          }
+        }
+      };
+#pragma unroll 1
+      for (int r = 0; r < kSub; ++r) {
+        const int2 rt = runtab[r];
+        if (rt.y == 0) {
+          if (lane < 2) {
+            pm[r * 2 + lane] = 0.0f;
+          }
+          continue;
+        }
+        const float4* rb = reinterpret_cast<const float4*>(B + rt.x);
+        const int     n4 = rt.y >> 1; // float4 = 2 entries
+        do_chunks(r, true, r, rb, n4, rt.y); // the sub-bucket's own bins (first chunk: moment lanes)
+        if (r + 1 < kSub && ((em >> (r + 1)) & 1u)) {
+          do_chunks(r + 1, false, r, rb, n4, rt.y); // a threshold of sub-bucket r + 1 strays down here
+        }
+        if (r > 0 && ((em >> (kSub + r - 1)) & 1u)) {
+          do_chunks(r - 1, false, r, rb, n4, rt.y); // a threshold of sub-bucket r - 1 strays up here
+        }
       }
-      if (col == 0 && lane < 2) {
-        // moment lanes 0 / 1 of group 0 carry S0 / S1 of this piece
-        float* pm = reinterpret_cast<float*>(P.piece_mom + piece);
-        pm[lane] = s2p[0];
-      }
+      __syncwarp(); // every lane is done with B before the next piece's scatter
+      piece = npiece;
+      b     = nbk;
+      beg   = nbeg;
+      end   = nend;
     }
     if (lane == 0 && lane_evals != 0ull) {
       atomicAdd(P.lane_evals, lane_evals);
     }
-
-    // ---- CTA reduction over the warps of a column (fixed order), one partial row per CTA
-    const int rows = kPWarps / P.ncols;
-    const int row  = warp / P.ncols;
-#pragma unroll
-    for (int g = 0; g < GPW; ++g) {
-      red[(warp * GPW + g) * 32 + lane] = accd[g];
-    }
+    // ---- the CTA's eight warp rows -> one row, in warp order (the reductions above were
+    // performed at L2; the loads below bypass L1)
+    __threadfence();
     __syncthreads();
-    if (row == 0) {
+    const double* rows = P.partials + (std::size_t)blockIdx.x * kPWarps * P.nslots;
+    for (int j = tid; j < P.nslots; j += kPThreads) {
+      double s = 0.0;
 #pragma unroll
-      for (int g = 0; g < GPW; ++g) {
-        double s = 0.0;
-        for (int r = 0; r < rows; ++r) {
-          s += red[((r * P.ncols + col) * GPW + g) * 32 + lane];
-        }
-        P.partials[(std::size_t)blockIdx.x * P.nslots + (col * GPW + g) * 32 + lane] = s;
+      for (int w = 0; w < kPWarps; ++w) {
+        s += __ldcg(rows + (std::size_t)w * P.nslots + j);
       }
+      P.cta_partials[(std::size_t)blockIdx.x * P.nslots + j] = s;
     }
   }
-
-  // msum[b] = S0 of bucket b, msum[nb + b] = S1: fp64 sums over the bucket's pieces,
-  // lane-strided then a fixed shuffle tree.  Also counts (roofline accounting, integer
-  // atomics) the pairs of the bucket whose cell pair is not identically zero: what an
-  // ideal kernel would have to evaluate.
+  // msum[b * (kSub + 1) + a] = {sum_{s >= a} S0_{b,s}, sum_{s >= a} S1_{b,s}}: suffix sums over the
+  // sub-buckets of bucket b (a = 0: the whole bucket, a = kSub: 0) of the fp64 sums over the
+  // bucket's pieces, lane-strided then a fixed shuffle tree.  Also counts (roofline accounting,
+  // integer atomics) the pairs of the bucket whose cell pair is not identically zero: what an
+  // ideal kernel evaluating every pair would have to touch.
   __global__ void __launch_bounds__(kPThreads)
-    pair_moments_kernel(const int* __restrict__ tot, int nb, const float2* __restrict__ piece_mom,
-                        double* __restrict__ msum, const int2* __restrict__ slot_i,
+    pair_moments_kernel(const int* __restrict__ tot, int nb, const float* __restrict__ piece_mom,
+                        double2* __restrict__ msum, const int2* __restrict__ slot_i,
                         const int* __restrict__ bin_of_slot, const float4* __restrict__ coef_dh,
                         int nslots, unsigned long long* __restrict__ ontable) {
     __shared__ int bstart[kPMaxBuckets + 2], pstart[kPMaxBuckets + 2], tmp[2 * kPWarps];
@@ -991,11 +1069,24 @@ namespace rgc {
     if (b >= nb) {
       return;
     }
-    double s0 = 0.0, s1 = 0.0;
+    double s0[kSub], s1[kSub];
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) {
+      s0[s] = 0.0;
+      s1[s] = 0.0;
+    }
     for (int p = pstart[b] + lane; p < pstart[b + 1]; p += 32) {
-      const float2 m = piece_mom[p];
-      s0 += (double)m.x;
-      s1 += (double)m.y;
+      const float4* m4 = reinterpret_cast<const float4*>(piece_mom + (std::size_t)p * kMomStride);
+#pragma unroll
+      for (int h = 0; h < kMomStride / 4; ++h) {
+        const float4 m = m4[h];
+        s0[2 * h] += (double)m.x;
+        s1[2 * h] += (double)m.y;
+        if (2 * h + 1 < kSub) {
+          s0[2 * h + 1] += (double)m.z;
+          s1[2 * h + 1] += (double)m.w;
+        }
+      }
     }
     int live = 0;
     for (int sl = lane; sl < nslots; sl += 32) {
@@ -1003,25 +1094,41 @@ namespace rgc {
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-      s0 += __shfl_xor_sync(0xffffffffu, s0, off);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+#pragma unroll
+      for (int s = 0; s < kSub; ++s) {
+        s0[s] += __shfl_xor_sync(0xffffffffu, s0[s], off);
+        s1[s] += __shfl_xor_sync(0xffffffffu, s1[s], off);
+      }
       live += __shfl_xor_sync(0xffffffffu, live, off);
     }
     if (lane == 0) {
-      msum[b]      = s0;
-      msum[nb + b] = s1;
+      double2* out = msum + (std::size_t)b * (kSub + 1);
+      double   a0 = 0.0, a1 = 0.0;
+      out[kSub]   = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int s = kSub - 1; s >= 0; --s) {
+        a0 += s0[s];
+        a1 += s1[s];
+        out[s] = make_double2(a0, a1);
+      }
       if (tot[b] != 0 && live != 0) {
         atomicAdd(ontable, (unsigned long long)tot[b] * (unsigned long long)live);
       }
     }
   }
 
-  // out[slot] = sum_cta hinge partials + sum_b ( v_q S0_b + s_q (fa S0_b + S1_b) );
+  // out[slot] = sum_rows hinge partials
+  //           + sum_b ( v_q S0_b + s_q (fa S0_b + S1_b) )                       line part
+  //           + sum_b ds_q * ( S1_{b,>pw} + fa' S0_{b,>pw} )                    hinge, sub-buckets above
+  //             the bin's threshold (r = fc + fa' there; sub-buckets below contribute 0), or, for the
+  //             cell pair next to the zero tail, ds_q * ( (1 - fa) S0_{b,<pw} - S1_{b,<pw} );
   // one warp per slot, lane-strided sums and a fixed shuffle tree
   __global__ void __launch_bounds__(kPThreads)
-    pair_final_kernel(const double* __restrict__ partials, int nctas, int nslots,
+    pair_final_kernel(const double* __restrict__ partials, int nrows, int nslots,
                       const int2* __restrict__ slot_i, const float2* __restrict__ slot_f,
-                      const double2* __restrict__ coef_vs, const double* __restrict__ msum,
+                      const int* __restrict__ slot_sub, const unsigned* __restrict__ extmask,
+                      const float4* __restrict__ coef_dh,
+                      const double2* __restrict__ coef_vs, const double2* __restrict__ msum,
                       int nb, double* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int j    = blockIdx.x * kPWarps + (threadIdx.x >> 5);
@@ -1029,16 +1136,35 @@ namespace rgc {
       return;
     }
     double s = 0.0;
-    for (int c = lane; c < nctas; c += 32) {
+    for (int c = lane; c < nrows; c += 32) {
       s += partials[(std::size_t)c * nslots + j];
     }
-    const int2   si = slot_i[j];
-    const double fa = (double)slot_f[j].x;
+    const int2   si  = slot_i[j];
+    const float  faf = slot_f[j].x;
+    const double fa  = (double)faf;
+    const int    s0  = slot_sub[j]; // the sub-bucket of the bin's hinge threshold
     if (si.x >= 0) {
       for (int b = lane; b < nb; b += 32) {
-        const double2 vs = coef_vs[si.x + b];
-        const double  S0 = msum[b], S1 = msum[nb + b];
-        s += fma(vs.x, S0, vs.y * fma(fa, S0, S1));
+        const double2* mb = msum + (std::size_t)b * (kSub + 1);
+        const double2  vs = coef_vs[si.x + b];
+        const float4   dh = coef_dh[si.x + b];
+        const double2  m0 = mb[0];
+        double         t  = fma(vs.x, m0.x, vs.y * fma(fa, m0.x, m0.y));
+        if (dh.x != 0.0f) {
+          // sub-buckets [pw_lo, pw_hi] were evaluated pair by pair for this bucket
+          const unsigned em    = extmask[b];
+          const int      pw_lo = s0 - (int)((em >> s0) & 1u);
+          const int      pw_hi = s0 + (int)((em >> (kSub + s0)) & 1u);
+          if (dh.z > 0.0f) {
+            const float   fap = faf - dh.y; // the pair kernel's float fa'
+            const double2 ma  = mb[pw_hi + 1];
+            t = fma((double)dh.x, fma((double)fap, ma.x, ma.y), t);
+          } else {
+            const double2 mlo = mb[pw_lo];
+            t = fma((double)dh.x, fma(1.0 - fa, m0.x - mlo.x, -(m0.y - mlo.y)), t);
+          }
+        }
+        s += t;
       }
     }
 #pragma unroll
@@ -1049,20 +1175,26 @@ namespace rgc {
       out[j] = s;
     }
   }
-
   // ------------------------------------------------------------------ host side
   struct PairPlan {
     std::vector<int2>    slot_i;
     std::vector<float2>  slot_f;
+    std::vector<int>     slot_sub; // sub-bucket of the slot's lane group
     std::vector<float4>  coef_dh;
     std::vector<double2> coef_vs;
     std::vector<int>     bin_of_slot;
-    int    ncols { 1 }, gpw { 1 }, nslots { 0 }, n_pad { 0 }, nb { 0 }, nbp { 0 }, kmin { 0 };
+    std::vector<int4>    chunks;   // {first lane group, groups, carries the moment lanes, -}
+    std::vector<unsigned char> na_tab; // [bucket][chunk] leading groups of the chunk on the table
+    std::vector<unsigned>      extmask; // [bucket] sub-buckets that also see a neighbouring run
+    int    chunk_first[kSub + 1] {};
+    int    ngroups { 0 }, nslots { 0 }, n_pad { 0 }, nb { 0 }, nbp { 0 }, kmin { 0 };
     double c0 { 0 }, c_lo { 0 }, c_hi { 0 };
+    float  sub_phi { 0 };          // s = floor(kSubDiv fc + sub_phi)
+    bool   ok { true };            // false: a hinge threshold strays beyond the neighbouring sub-bucket
   };
 
-  bool pair_path_eligible(const TablePlan& tp, const float* bins_e_syn,
-                          const std::vector<int>& bins) {
+  static bool pair_shape_eligible(const TablePlan& tp, const float* bins_e_syn,
+                                  const std::vector<int>& bins) {
     if (bins.empty() || (int)bins.size() > kPMaxBins) {
       return false;
     }
@@ -1133,48 +1265,154 @@ namespace rgc {
                                     (float)(tp.tx[k + 1] - (double)k), 1.0f, 0.0f);
       }
     }
-    // slots: every warp column keeps its first two lanes for the moments S0 / S1 (group 0
-    // always runs in column 0; trailing groups are skipped when all their lanes sit on
-    // zero cells)
-    const int cap1 = kPMaxGPW * 32 - 2;
-    pp.ncols       = 1;
-    while (pp.ncols < 8 && (nbin + pp.ncols - 1) / pp.ncols > cap1) {
-      pp.ncols *= 2;
-    }
-    const int per_col = (nbin + pp.ncols - 1) / pp.ncols;
-    pp.gpw            = (per_col + 2 + 31) / 32;
-    pp.nslots         = pp.ncols * pp.gpw * 32;
-    // spare slots sit on padded cell 0 = {0, h = 1, +1}:  fa' = fa0 - 1
-    pp.slot_i.assign(pp.nslots, make_int2(-(1 << 20), 0));
-    pp.slot_f.assign(pp.nslots, make_float2(1.0f, 0.0f));
-    pp.bin_of_slot.assign(pp.nslots, -1);
-    // bins in ascending energy, dealt round-robin to the warp columns: every column then
-    // spans the whole energy range with ascending lanes (so the groups a bucket cannot
-    // reach are its TRAILING ones, in every column alike, and the columns' costs balance)
+    // ---- bins by the sub-bucket of their hinge threshold.  For a particle of fraction fc the
+    // hinge of bin j (fraction fa, node at h ~ 1) is active for fc > h - fa; the bin goes to
+    // sub-bucket s0 = floor(kSubDiv (1 - fa) + phi).  The phase phi puts the sub-bucket boundaries
+    // into the widest gap between the thresholds (bin grids commensurate with the table grid --
+    // 200 bins over 7 decades on the 200-point table over 8 -- put every threshold on a multiple
+    // of 1/8).  Every sub-bucket owns whole lane groups; the
+    // first two lanes of its first group are the moment lanes (S0: fa0 = 2 -> r = 1,
+    // S1: fa0 = 1 -> r = fc; a sub-bucket without bins still gets them).  Inside a
+    // sub-bucket the bins ascend in energy, so the groups a bucket cannot reach are the
+    // trailing ones.
+    struct BinSlot {
+      int    bin, A, s0;
+      float  fa;
+      double a;
+    };
     std::vector<int> order(nbin);
     for (int s = 0; s < nbin; ++s) {
       order[s] = s;
     }
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return a[x] < a[y]; });
-    for (int k = 0; k < nbin; ++k) {
-      const int    s    = order[k];
-      const int    c    = k % pp.ncols, r = k / pp.ncols;
-      const int    slot = c * pp.gpw * 32 + 2 + r;
-      const double rel  = a[s] - amin;
-      double       A    = std::floor(rel);
-      float        fa   = (float)(rel - A);
-      if (fa >= 1.0f) { // rounding of the fraction to float
-        fa = 0.0f;
-        A += 1.0;
+    std::vector<std::vector<BinSlot>> by_sub(kSub);
+    std::vector<float>                fa_of(nbin);
+    std::vector<double>               A_of(nbin);
+    {
+      std::vector<double> v(nbin); // position of the threshold inside its eighth
+      for (int s = 0; s < nbin; ++s) {
+        const double rel = a[s] - amin;
+        double       A   = std::floor(rel);
+        float        fa  = (float)(rel - A);
+        if (fa >= 1.0f) { // rounding of the fraction to float
+          fa = 0.0f;
+          A += 1.0;
+        }
+        fa_of[s]       = fa;
+        A_of[s]        = A;
+        const double t = (1.0 - (double)fa) * (double)kSubDiv;
+        v[s]           = t - std::floor(t);
       }
-      pp.slot_i[slot]      = make_int2((int)A + pp.kmin, 1);
-      pp.slot_f[slot]      = make_float2(fa, 1.0f);
-      pp.bin_of_slot[slot] = bins[s];
+      std::sort(v.begin(), v.end());
+      double best = -1.0, centre = 0.5;
+      for (int s = 0; s < nbin; ++s) { // circular gaps
+        const double lo = v[s], hi = s + 1 < nbin ? v[s + 1] : v[0] + 1.0;
+        if (hi - lo > best) {
+          best   = hi - lo;
+          centre = 0.5 * (lo + hi);
+        }
+      }
+      centre -= std::floor(centre);
+      // boundaries where kSubDiv t + phi is an integer, i.e. frac(kSubDiv t) = 1 - phi
+      double phi = 1.0 - centre;
+      phi -= std::floor(phi);
+      pp.sub_phi = (float)phi;
+      if (!(pp.sub_phi >= 0.0f && pp.sub_phi < 1.0f)) {
+        pp.sub_phi = 0.0f;
+      }
     }
-    for (int c = 0; c < pp.ncols; ++c) {
-      const int first = c * pp.gpw * 32;
-      pp.slot_f[first]     = make_float2(2.0f, 0.0f); // r = sat(1 + fc) = 1   -> S0
-      pp.slot_f[first + 1] = make_float2(1.0f, 0.0f); // r = sat(fc)     = fc  -> S1
+    const double phi = (double)pp.sub_phi;
+    for (int k = 0; k < nbin; ++k) {
+      const int    s  = order[k];
+      const float  fa = fa_of[s];
+      const double A  = A_of[s];
+      int s0 = (int)std::floor((1.0 - (double)fa) * (double)kSubDiv + phi);
+      s0     = std::max(0, std::min(kSub - 1, s0));
+      by_sub[s0].push_back(BinSlot { bins[s], (int)A + pp.kmin, s0, fa, a[s] });
+    }
+    int first_group[kSub + 1];
+    first_group[0] = 0;
+    for (int s = 0; s < kSub; ++s) {
+      first_group[s + 1] = first_group[s] + ((int)by_sub[s].size() + 2 + 31) / 32;
+    }
+    pp.ngroups = first_group[kSub];
+    pp.nslots  = pp.ngroups * 32;
+    // spare slots sit on padded cell 0 (the kernel gives them fa' = fa0 - 1 and ds = 0)
+    pp.slot_i.assign(pp.nslots, make_int2(-(1 << 20), 0));
+    pp.slot_f.assign(pp.nslots, make_float2(1.0f, 0.0f));
+    pp.slot_sub.assign(pp.nslots, 0);
+    pp.bin_of_slot.assign(pp.nslots, -1);
+    // ---- per bucket: which neighbouring run a sub-bucket's groups must also see (the float
+    // threshold -fa' = h_q - fa of an L cell wanders with the node position h_q, 1 +- 1e-5, and
+    // may leave the bin's nominal sub-bucket by a hair), and which lane groups are on the table
+    pp.extmask.assign(pp.nb, 0u);
+    std::vector<unsigned char> group_live((std::size_t)pp.nb * pp.ngroups, 0);
+    pp.ok = true;
+    for (int s = 0; s < kSub; ++s) {
+      const int base = first_group[s] * 32;
+      pp.slot_f[base]     = make_float2(2.0f, 0.0f); // r = sat(1 + fc) = 1 -> S0
+      pp.slot_f[base + 1] = make_float2(1.0f, 0.0f); // r = sat(fc)     = fc -> S1
+      for (int g = first_group[s]; g < first_group[s + 1]; ++g) {
+        for (int l = 0; l < 32; ++l) {
+          pp.slot_sub[g * 32 + l] = s;
+        }
+      }
+      for (std::size_t k = 0; k < by_sub[s].size(); ++k) {
+        const BinSlot& bs   = by_sub[s][k];
+        const int      slot = base + 2 + (int)k;
+        pp.slot_i[slot]      = make_int2(bs.A, 1);
+        pp.slot_f[slot]      = make_float2(bs.fa, 1.0f);
+        pp.bin_of_slot[slot] = bs.bin;
+        for (int b = 0; b < pp.nb; ++b) {
+          const float4 dh = pp.coef_dh[std::max(bs.A + b, 0)];
+          if (dh.x == 0.0f) {
+            continue; // zero cell pair
+          }
+          group_live[(std::size_t)b * pp.ngroups + slot / 32] = 1;
+          // threshold in fc: the hinge of an L cell is active for fc > -fa' (the kernel's float
+          // fa'), the zero-tail form changes at fc = 1 - fa.  Sub-buckets below the evaluated
+          // range must lie entirely on one side, those above entirely on the other; eps covers
+          // the float rounding of the kernel's floor(kSubDiv fc + phi)
+          const double tt  = dh.z < 0.0f ? 1.0 - (double)bs.fa : -(double)(bs.fa - dh.y);
+          const double eps = 1e-6;
+          auto edge = [&](int k) { return ((double)k - phi) / (double)kSubDiv; }; // lower edge of sub-bucket k
+          if (s > 0 && tt < edge(s) + eps) {
+            pp.extmask[b] |= 1u << s;
+            if (s > 1 && tt < edge(s - 1) + eps) {
+              pp.ok = false;
+            }
+          }
+          if (s < kSub - 1 && tt > edge(s + 1) - eps) {
+            pp.extmask[b] |= 1u << (kSub + s);
+            if (s < kSub - 2 && tt > edge(s + 2) - eps) {
+              pp.ok = false;
+            }
+          }
+        }
+      }
+    }
+    // ---- chunks of <= kPMaxGPW groups
+    pp.chunks.clear();
+    for (int s = 0; s < kSub; ++s) {
+      pp.chunk_first[s] = (int)pp.chunks.size();
+      for (int g = first_group[s]; g < first_group[s + 1]; g += kPMaxGPW) {
+        pp.chunks.push_back(make_int4(g, std::min(kPMaxGPW, first_group[s + 1] - g),
+                                      g == first_group[s] ? 1 : 0, 0));
+      }
+    }
+    pp.chunk_first[kSub] = (int)pp.chunks.size();
+    const int nchunks = (int)pp.chunks.size();
+    pp.na_tab.assign((std::size_t)pp.nb * nchunks, 0);
+    for (int b = 0; b < pp.nb; ++b) {
+      for (int c = 0; c < nchunks; ++c) {
+        int na = pp.chunks[c].z ? 1 : 0; // the moment lanes always run
+        for (int g = 0; g < pp.chunks[c].y; ++g) {
+          if (group_live[(std::size_t)b * pp.ngroups + pp.chunks[c].x + g]) {
+            na = g + 1;
+          }
+        }
+        pp.na_tab[(std::size_t)b * nchunks + c] = (unsigned char)na;
+      }
     }
   }
 
@@ -1187,6 +1425,7 @@ namespace rgc {
     PairPlan            pp;
     char*               dev { nullptr };
     std::size_t         off_map { 0 }, off_si { 0 }, off_sf { 0 }, off_dh { 0 }, off_vs { 0 };
+    std::size_t         off_sub { 0 }, off_chunk { 0 }, off_na { 0 }, off_ext { 0 };
   };
   static std::vector<CachedPlan>& plan_cache() {
     static std::vector<CachedPlan> cache;
@@ -1257,7 +1496,11 @@ namespace rgc {
     e.off_sf  = align(e.off_si + pp.nslots * sizeof(int2));
     e.off_dh  = align(e.off_sf + pp.nslots * sizeof(float2));
     e.off_vs  = align(e.off_dh + pp.n_pad * sizeof(float4));
-    const std::size_t total = align(e.off_vs + pp.n_pad * sizeof(double2));
+    e.off_sub   = align(e.off_vs + pp.n_pad * sizeof(double2));
+    e.off_chunk = align(e.off_sub + pp.nslots * sizeof(int));
+    e.off_na    = align(e.off_chunk + pp.chunks.size() * sizeof(int4));
+    e.off_ext   = align(e.off_na + pp.na_tab.size());
+    const std::size_t total = align(e.off_ext + pp.extmask.size() * sizeof(unsigned));
     RGC_CUDA(cudaMalloc(reinterpret_cast<void**>(&e.dev), total));
     cudaStream_t st = ctx().stream;
     RGC_CUDA(cudaMemcpyAsync(e.dev + e.off_map, pp.bin_of_slot.data(), pp.nslots * sizeof(int),
@@ -1270,9 +1513,31 @@ namespace rgc {
                              cudaMemcpyHostToDevice, st));
     RGC_CUDA(cudaMemcpyAsync(e.dev + e.off_vs, pp.coef_vs.data(), pp.n_pad * sizeof(double2),
                              cudaMemcpyHostToDevice, st));
+    RGC_CUDA(cudaMemcpyAsync(e.dev + e.off_sub, pp.slot_sub.data(), pp.nslots * sizeof(int),
+                             cudaMemcpyHostToDevice, st));
+    RGC_CUDA(cudaMemcpyAsync(e.dev + e.off_chunk, pp.chunks.data(), pp.chunks.size() * sizeof(int4),
+                             cudaMemcpyHostToDevice, st));
+    RGC_CUDA(cudaMemcpyAsync(e.dev + e.off_na, pp.na_tab.data(), pp.na_tab.size(),
+                             cudaMemcpyHostToDevice, st));
+    RGC_CUDA(cudaMemcpyAsync(e.dev + e.off_ext, pp.extmask.data(), pp.extmask.size() * sizeof(unsigned),
+                             cudaMemcpyHostToDevice, st));
     cache.push_back(std::move(e));
     *out = &cache.back();
     return RGC_OK;
+  }
+
+  // The hinge path takes a chunk of bins when its shape fits and the plan keeps every hinge
+  // threshold within one sub-bucket of its nominal place (always, for tables on a log grid).
+  bool pair_path_eligible(const TablePlan& tp, const float* bins_e_syn,
+                          const std::vector<int>& bins) {
+    if (!pair_shape_eligible(tp, bins_e_syn, bins)) {
+      return false;
+    }
+    const CachedPlan* cp = nullptr;
+    if (cached_pair_plan(tp, bins_e_syn, bins, &cp) != RGC_OK) {
+      return false;
+    }
+    return cp->pp.ok && cp->pp.ngroups <= kPMaxGroups;
   }
 
   // Runs rank_order_probe_kernel once per process (per device context) and remembers the verdict.
@@ -1311,29 +1576,6 @@ namespace rgc {
 
   bool pair_single_pass(std::size_t n) { return n <= pair_pass_max(); }
 
-  template <int G>
-  static int launch_pair_g(dim3 grid, std::size_t smem, cudaStream_t st, const PairParams& P) {
-    auto kern = sync_pair_kernel<G>;
-    RGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kPThreads, smem, st>>>(P);
-    return RGC_OK;
-  }
-
-  static int launch_pair(int gpw, dim3 grid, std::size_t smem, cudaStream_t st,
-                         const PairParams& P) {
-    switch (gpw) {
-      case 1: return launch_pair_g<1>(grid, smem, st, P);
-      case 2: return launch_pair_g<2>(grid, smem, st, P);
-      case 3: return launch_pair_g<3>(grid, smem, st, P);
-      case 4: return launch_pair_g<4>(grid, smem, st, P);
-      case 5: return launch_pair_g<5>(grid, smem, st, P);
-      case 6: return launch_pair_g<6>(grid, smem, st, P);
-      case 7: return launch_pair_g<7>(grid, smem, st, P);
-      case 8: return launch_pair_g<8>(grid, smem, st, P);
-    }
-    return fail(RGC_ERR_INVALID, "internal: bad groups per warp %d", gpw);
-  }
-
   // One pipeline pass per <= 2^27 particles over one chunk of bins.
   // d_acc[bins[s]] += sum_i w_i F_is (before the e_syn factor), on the device;
   // *d_poison is raised when a particle's chiR overflows float (see pair_prologue).
@@ -1348,9 +1590,9 @@ namespace rgc {
     if (pp.nb >= kPMaxBuckets || pp.nbp > kPMaxBuckets) {
       return fail(RGC_ERR_INVALID, "internal: %d buckets exceed the pair path's limit", pp.nb);
     }
-    const PairSmem    L    = pair_smem_layout(pp.n_pad, pp.nbp, pp.gpw);
+    const PairSmem    L    = pair_smem_layout(pp.n_pad, pp.nbp, pp.nslots, (int)pp.chunks.size());
     const std::size_t smem = L.total;
-    if (smem > 113 * 1024) {
+    if (smem > 226 * 1024) {
       return fail(RGC_ERR_INVALID, "internal: pair kernel needs %zu B of shared memory", smem);
     }
     // particles are processed in passes so the staged and sorted (fc, w, key) stay
@@ -1383,16 +1625,24 @@ namespace rgc {
     const Geom        g0    = geom_for(cnt0);
     const int         rows0 = g0.rows;
     const std::size_t npad0 = (std::size_t)g0.ntiles * kPTile;
-    const int         pair_ctas   = c.sm_count * 2;
+    int max_groups = 1;
+    for (const int4& ch : pp.chunks) {
+      max_groups = std::max(max_groups, ch.y);
+    }
+    const bool small_na = max_groups <= 2; // the 3-CTA-per-SM instantiation
+    const int  pair_ctas_per_sm = (small_na && 3 * (smem + 1024) <= 227 * 1024) ? 3 : 2;
+    const int  pair_ctas        = c.sm_count * pair_ctas_per_sm;
     const std::size_t max_pieces  = cnt0 / kPieceLen + (std::size_t)pp.nbp + 2;
     auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
     const std::size_t off_msum = 0;
-    const std::size_t off_out  = align(off_msum + 2 * pp.nb * sizeof(double));
-    const std::size_t off_part = align(off_out + pp.nslots * sizeof(double));
-    const std::size_t off_tot  = align(off_part + (std::size_t)pair_ctas * pp.nslots * sizeof(double));
+    const std::size_t off_out  = align(off_msum + (std::size_t)pp.nb * (kSub + 1) * sizeof(double2));
+    const std::size_t off_cpart = align(off_out + pp.nslots * sizeof(double));
+    const std::size_t off_part = align(off_cpart + (std::size_t)pair_ctas * pp.nslots * sizeof(double));
+    const std::size_t part_bytes = (std::size_t)pair_ctas * kPWarps * pp.nslots * sizeof(double);
+    const std::size_t off_tot  = align(off_part + part_bytes);
     const std::size_t off_cnt  = align(off_tot + (std::size_t)pp.nbp * sizeof(int));
     const std::size_t off_mom  = align(off_cnt + (std::size_t)pp.nbp * rows0 * sizeof(int));
-    const std::size_t off_cw   = align(off_mom + max_pieces * sizeof(float2));
+    const std::size_t off_cw   = align(off_mom + max_pieces * kMomStride * sizeof(float));
     const std::size_t off_keys = align(off_cw + npad0 * sizeof(float2));
     const std::size_t off_sort = align(off_keys + npad0 * sizeof(unsigned short));
     const std::size_t total    = off_sort + (cnt0 + pp.nbp + 64) * sizeof(float2);
@@ -1409,7 +1659,14 @@ namespace rgc {
     P.n_pad    = pp.n_pad;
     P.nb       = pp.nb;
     P.nbp      = pp.nbp;
-    P.ncols    = pp.ncols;
+    P.chunks   = reinterpret_cast<const int4*>(cp->dev + cp->off_chunk);
+    P.na_tab   = reinterpret_cast<const unsigned char*>(cp->dev + cp->off_na);
+    P.extmask  = reinterpret_cast<const unsigned*>(cp->dev + cp->off_ext);
+    P.nchunks  = (int)pp.chunks.size();
+    P.sub_phi  = pp.sub_phi;
+    for (int r = 0; r <= kSub; ++r) {
+      P.chunk_first[r] = pp.chunk_first[r];
+    }
     P.kmin     = pp.kmin;
     P.kmin_d   = (double)pp.kmin;
     P.inv_B0           = 1.0 / (double)B0;
@@ -1426,16 +1683,21 @@ namespace rgc {
     P.poison    = d_poison;
     {
       const char* ns  = std::getenv("RGC_PAIR_NO_SKIP"); // test knob
-      P.force_groups  = (ns && ns[0] == '1') ? ((1u << pp.gpw) - 1u) : 0u;
+      P.force_groups  = (ns && ns[0] == '1') ? 1u : 0u;
     }
     P.lane_evals = reinterpret_cast<unsigned long long*>(d_poison) + 1; // [issued, on-table] behind the flag
     P.sorted    = reinterpret_cast<float2*>(sb + off_sort);
-    P.piece_mom = reinterpret_cast<float2*>(sb + off_mom);
+    P.piece_mom = reinterpret_cast<float*>(sb + off_mom);
     P.partials  = reinterpret_cast<double*>(sb + off_part);
+    P.cta_partials = reinterpret_cast<double*>(sb + off_cpart);
     P.nslots    = pp.nslots;
     P.o_coef = (int)L.coef; P.o_bstart = (int)L.bstart; P.o_pstart = (int)L.pstart;
-    P.o_tmp = (int)L.tmp; P.o_ring = (int)L.ring; P.o_mbar = (int)L.mbar; P.o_red = (int)L.red;
-    double* d_msum = reinterpret_cast<double*>(sb + off_msum);
+    P.o_tmp = (int)L.tmp; P.o_slot = (int)L.slot; P.o_chunk = (int)L.chunk;
+    P.o_warp = (int)L.warp; P.warp_stride = (int)L.warp_stride;
+    double2* d_msum = reinterpret_cast<double2*>(sb + off_msum);
+    RGC_CUDA(cudaFuncSetAttribute(sync_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RGC_CUDA(cudaFuncSetAttribute(sync_pair_kernel<kPMaxGPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
     double* d_out  = reinterpret_cast<double*>(sb + off_out);
     float               pro_ms = 0.f, sort_ms = 0.f;
     const std::size_t   sort_smem = sort_smem_layout(pp.nbp).total;
@@ -1475,7 +1737,12 @@ namespace rgc {
       }
       RGC_CUDA(cudaGetLastError());
       RGC_CUDA(cudaEventRecord(c.ev[5], c.stream));
-      RGC_TRY(launch_pair(pp.gpw, dim3(pair_ctas), smem, c.stream, P));
+      RGC_CUDA(cudaMemsetAsync(P.partials, 0, part_bytes, c.stream));
+      if (small_na) {
+        sync_pair_kernel<2><<<pair_ctas, kPThreads, smem, c.stream>>>(P);
+      } else {
+        sync_pair_kernel<kPMaxGPW><<<pair_ctas, kPThreads, smem, c.stream>>>(P);
+      }
       RGC_CUDA(cudaGetLastError());
       RGC_CUDA(cudaEventRecord(c.ev[4], c.stream));
       pair_moments_kernel<<<(pp.nb + kPWarps - 1) / kPWarps, kPThreads, 0, c.stream>>>(
@@ -1483,7 +1750,8 @@ namespace rgc {
         P.coef_dh, pp.nslots, P.lane_evals + 1);
       RGC_CUDA(cudaGetLastError());
       pair_final_kernel<<<(pp.nslots + kPWarps - 1) / kPWarps, kPThreads, 0, c.stream>>>(
-        P.partials, pair_ctas, pp.nslots, P.slot_i, P.slot_f,
+        P.cta_partials, pair_ctas, pp.nslots, P.slot_i, P.slot_f,
+        reinterpret_cast<const int*>(cp->dev + cp->off_sub), P.extmask, P.coef_dh,
         reinterpret_cast<const double2*>(cp->dev + cp->off_vs), d_msum, pp.nb, d_out);
       RGC_CUDA(cudaGetLastError());
       count_launch(6);
