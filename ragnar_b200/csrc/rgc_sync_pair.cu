@@ -75,14 +75,15 @@ namespace rgc {
   constexpr int kSubDiv      = 8;    // a table cell is cut into eighths of the fraction fc ...
   constexpr int kSub         = kSubDiv + 1; // ... shifted by the plan's phase: 9 sub-buckets, s = floor(8 fc + phi)
   constexpr int kMomStride   = 2 * kSub + 2; // floats per piece in piece_mom (16-byte multiple)
+  constexpr int kSubPk       = (kSub + 1) / 2; // sub-bucket counters packed two to a register
   constexpr int kPMaxBins    = 2032; // per launch
   constexpr int kPMaxGroups  = 96;   // lane groups per launch (bins by sub-bucket + moment lanes)
   constexpr int kPMaxBuckets = 1024;
   constexpr unsigned kInvalidKey = 0xffffu;
   constexpr int kPTile       = 4096; // particles per tile of the prologue / sort kernels
   constexpr int kPSteps      = kPTile / kPThreads;
-  constexpr int kPieceLen    = 512;  // sorted entries per work unit of the pair kernel
-  constexpr int kPieceEnt    = kPieceLen / 32; // entries per lane in the piece's sub-sort
+  constexpr int kPieceLen    = 4096; // sorted entries per work unit (one CTA) of the pair kernel
+  constexpr int kPieceEnt    = kPieceLen / kPThreads; // entries per thread in the piece's sub-sort
 
   // fp64 constants of the prologue, read as constant-bank operands (an immediate double
   // whose low word is not zero costs two UMOVs per use otherwise)
@@ -124,25 +125,21 @@ namespace rgc {
     int*        poison;    // != 0: a particle's chiR overflows float (see pair_prologue)
     unsigned long long* lane_evals; // hinge evaluations the pair kernel issued (roofline accounting)
     unsigned force_groups;          // != 0: lane groups are evaluated even when all their lanes sit on zero cells
-    double*     partials;  // [warp of the grid][nslots] hinge sums (RED.ADD.F64 targets, zeroed per pass)
-    double*     cta_partials; // [cta][nslots]: the CTA's warp rows summed in warp order
+    double*     partials;  // [cta][nslots] hinge sums (RED.ADD.F64 targets, zeroed per pass; a slot is
+                           // only ever touched by one warp of the CTA: the order of additions is fixed)
     int         nslots;
     // shared-memory layout of the pair kernel (byte offsets, computed once on the host)
-    int o_coef, o_bstart, o_pstart, o_tmp, o_slot, o_chunk, o_warp, warp_stride;
+    int o_coef, o_bstart, o_pstart, o_tmp, o_slot, o_chunk, o_sorted, o_cur, o_wtot, o_run;
   };
 
   __host__ __device__ inline std::size_t pair_align16(std::size_t x) { return (x + 15) & ~std::size_t(15); }
 
   struct PairSmem {
-    std::size_t coef, bstart, pstart, tmp, slot, chunk, warp, warp_stride, total;
+    std::size_t coef, bstart, pstart, tmp, slot, chunk, sorted, cur, wtot, run, total;
   };
-  // per-warp region of the pair kernel: the piece sorted by sub-bucket (every run padded to a
-  // multiple of 8 entries), the per-lane cursors of the sort, the run table
-  constexpr std::size_t kPWarpB      = 0;
-  constexpr std::size_t kPWarpCur    = kPWarpB + (std::size_t)(kPieceLen + 8 * kSub) * sizeof(float2);
-  constexpr std::size_t kPWarpRun    = kPWarpCur + (std::size_t)kSub * 32 * sizeof(int);
-  constexpr std::size_t kPWarpStride = (kPWarpRun + (std::size_t)kSub * sizeof(int2) + 127) & ~std::size_t(127);
-
+  // shared memory of the pair kernel: plan tables, the piece sorted by sub-bucket (every run
+  // padded to a multiple of 8 entries), the per-thread cursors of the sort, packed warp totals,
+  // the run table
   __host__ __device__ inline PairSmem pair_smem_layout(int n_pad, int nbp, int nslots, int nchunks) {
     PairSmem L;
     std::size_t o = 0;
@@ -152,10 +149,12 @@ namespace rgc {
     L.tmp = o;     o = pair_align16(o + (std::size_t)(2 * kPWarps) * sizeof(int));
     L.slot = o;    o = pair_align16(o + (std::size_t)nslots * sizeof(int2));
     L.chunk = o;   o = pair_align16(o + (std::size_t)nchunks * sizeof(int4));
+    L.wtot = o;    o = pair_align16(o + (std::size_t)kPWarps * kSubPk * sizeof(unsigned));
+    L.run = o;     o = pair_align16(o + (std::size_t)kSub * sizeof(int2));
+    L.cur = o;     o = pair_align16(o + (std::size_t)kSub * kPThreads * sizeof(int));
     o = (o + 127) & ~std::size_t(127);
-    L.warp        = o;
-    L.warp_stride = kPWarpStride;
-    L.total       = o + (std::size_t)kPWarps * kPWarpStride;
+    L.sorted = o;  o = o + (std::size_t)(kPieceLen + 8 * kSub) * sizeof(float2);
+    L.total  = o;
     return L;
   }
 
@@ -800,15 +799,15 @@ namespace rgc {
     int*    tmp      = reinterpret_cast<int*>(smem_raw + P.o_tmp);
     int2*   slot_tab = reinterpret_cast<int2*>(smem_raw + P.o_slot);
     int4*   chunks   = reinterpret_cast<int4*>(smem_raw + P.o_chunk);
+    float2* B        = reinterpret_cast<float2*>(smem_raw + P.o_sorted);
+    int*    cur      = reinterpret_cast<int*>(smem_raw + P.o_cur);    // [kSub][kPThreads]
+    unsigned* wtot   = reinterpret_cast<unsigned*>(smem_raw + P.o_wtot); // [kPWarps][kSubPk] packed warp totals -> prefixes
+    int2*   runtab   = reinterpret_cast<int2*>(smem_raw + P.o_run);   // [kSub] {start, padded length}
 
     const int tid  = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int nb   = P.nb;
-    unsigned char* wbase  = smem_raw + P.o_warp + (std::size_t)warp * P.warp_stride;
-    float2*        B      = reinterpret_cast<float2*>(wbase + kPWarpB);
-    int*           cur    = reinterpret_cast<int*>(wbase + kPWarpCur);
-    int2*          runtab = reinterpret_cast<int2*>(wbase + kPWarpRun);
     for (int i = tid; i < P.n_pad; i += kPThreads) {
       coef[i] = P.coef_dh[i];
     }
@@ -821,9 +820,7 @@ namespace rgc {
     block_scan_buckets(P.tot, nb, bstart, pstart, tmp); // ends with __syncthreads()
 
     const int npieces = pstart[nb];
-    const int wstride = gridDim.x * kPWarps;
-    const int gwarp   = blockIdx.x * kPWarps + warp;
-    double*   prow    = P.partials + (std::size_t)gwarp * P.nslots;
+    double*   prow    = P.partials + (std::size_t)blockIdx.x * P.nslots;
     unsigned long long lane_evals = 0; // hinge evaluations issued by this warp
     // bucket and sorted range of a piece: first b with pstart[b + 1] > piece
     auto locate = [&](int piece, int& b, int& beg, int& end) {
@@ -840,19 +837,18 @@ namespace rgc {
       beg = bstart[lo] + (piece - pstart[lo]) * kPieceLen;
       end = min(beg + kPieceLen, bstart[lo + 1]);
     };
-    int piece = gwarp, b = 0, beg = 0, end = 0;
-    if (piece < npieces) {
+
+    for (int piece = blockIdx.x; piece < npieces; piece += gridDim.x) {
+      int b, beg, end;
       locate(piece, b, beg, end);
-    }
-    while (piece < npieces) {
       const int n = end - beg; // even, <= kPieceLen
-      // ---- 1. the piece: 16 coalesced 8-byte loads per lane, all in flight at once (entries
+      // ---- 1. the piece: 16 coalesced 8-byte loads per thread, all in flight at once (entries
       // beyond a short piece become zero-weight pads); the bucket's chunk table rides along
       float2        ent[kPieceEnt];
       const float2* src = P.sorted + beg;
 #pragma unroll
       for (int st = 0; st < kPieceEnt; ++st) {
-        const int e = st * 32 + lane;
+        const int e = st * kPThreads + tid;
         ent[st]     = e < n ? __ldcs(src + e) : make_float2(0.0f, 0.0f);
       }
       const unsigned       em     = P.extmask[b];
@@ -862,38 +858,78 @@ namespace rgc {
       for (int q = 0; q < 3; ++q) {
         na_reg[q] = q * 32 + lane < P.nchunks ? (unsigned)na_row[q * 32 + lane] : 0u;
       }
-      // ---- 2. counting sort by sub-bucket; a lane's entries and cursors are its own
-      // (5-bit per-lane counters of the 9 sub-buckets packed into one 64-bit register)
+      // ---- 2. counting sort of the piece by sub-bucket, in (thread, entry) order: per-thread
+      // 5-bit counters of the 9 sub-buckets packed into one 64-bit register, warp scans of the
+      // counters packed two to a register, warp totals through shared memory
       unsigned long long cnt = 0ull;
 #pragma unroll
       for (int st = 0; st < kPieceEnt; ++st) {
         const int s = min(kSub - 1, (int)fmaf(ent[st].x, (float)kSubDiv, P.sub_phi));
         cnt += 1ull << (5 * s);
       }
-      {
-        int run = 0;
+      unsigned pk[kSubPk], incl[kSubPk];
 #pragma unroll
-        for (int k = 0; k < kSub; ++k) {
-          const int c    = (int)((cnt >> (5 * k)) & 31ull);
-          int       incl = c;
+      for (int j = 0; j < kSubPk; ++j) {
+        const unsigned lo = (unsigned)((cnt >> (10 * j)) & 31ull);
+        const unsigned hi = 2 * j + 1 < kSub ? (unsigned)((cnt >> (10 * j + 5)) & 31ull) : 0u;
+        pk[j]   = lo | (hi << 16);
+        incl[j] = pk[j];
+      }
 #pragma unroll
-          for (int off = 1; off < 32; off <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) {
-              incl += t;
-            }
+      for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+        for (int j = 0; j < kSubPk; ++j) {
+          const unsigned t = __shfl_up_sync(0xffffffffu, incl[j], off);
+          if (lane >= off) {
+            incl[j] += t;
           }
-          const int tot      = __shfl_sync(0xffffffffu, incl, 31);
-          const int padded   = (tot + 7) & ~7; // whole groups of 4 float4
-          cur[k * 32 + lane] = run + incl - c;
-          if (lane == k) {
-            runtab[k] = make_int2(run, padded);
-          }
-          if (lane < padded - tot) {
-            B[run + tot + lane] = make_float2(0.0f, 0.0f); // zero-weight pad
-          }
-          run += padded;
         }
+      }
+      __syncthreads(); // the previous piece's runs are done: B, cur, wtot, runtab are free
+      if (lane == 31) {
+#pragma unroll
+        for (int j = 0; j < kSubPk; ++j) {
+          wtot[warp * kSubPk + j] = incl[j];
+        }
+      }
+      __syncthreads();
+      if (warp == 0) {
+        // exclusive prefix over the warps (packed), totals, padded run starts
+        unsigned tot_pk = 0u;
+        if (lane < kSubPk) {
+#pragma unroll
+          for (int w = 0; w < kPWarps; ++w) {
+            const unsigned t         = wtot[w * kSubPk + lane];
+            wtot[w * kSubPk + lane]  = tot_pk;
+            tot_pk += t;
+          }
+        }
+        const unsigned tp  = __shfl_sync(0xffffffffu, tot_pk, lane >> 1);
+        const int      tot = lane < kSub ? (int)((tp >> ((lane & 1) * 16)) & 0xffffu) : 0;
+        const int      pad = (tot + 7) & ~7; // whole groups of 4 float4
+        int            inc = pad;
+#pragma unroll
+        for (int off = 1; off < 16; off <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, off);
+          if (lane >= off) {
+            inc += t;
+          }
+        }
+        if (lane < kSub) {
+          const int start = inc - pad;
+          runtab[lane]    = make_int2(start, pad);
+          for (int i = tot; i < pad; ++i) {
+            B[start + i] = make_float2(0.0f, 0.0f); // zero-weight pad
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kSub; ++k) {
+        const unsigned sh = (k & 1) * 16;
+        const int base = runtab[k].x + (int)((wtot[warp * kSubPk + (k >> 1)] >> sh) & 0xffffu) +
+                         (int)(((incl[k >> 1] - pk[k >> 1]) >> sh) & 0xffffu);
+        cur[k * kPThreads + tid] = base;
       }
       {
         unsigned long long seen = 0ull;
@@ -902,16 +938,10 @@ namespace rgc {
           const int s    = min(kSub - 1, (int)fmaf(ent[st].x, (float)kSubDiv, P.sub_phi));
           const int rank = (int)((seen >> (5 * s)) & 31ull);
           seen += 1ull << (5 * s);
-          B[cur[s * 32 + lane] + rank] = ent[st];
+          B[cur[s * kPThreads + tid] + rank] = ent[st];
         }
       }
-      __syncwarp();
-      // the next piece of this warp
-      const int npiece = piece + wstride;
-      int       nbk = 0, nbeg = 0, nend = 0;
-      if (npiece < npieces) {
-        locate(npiece, nbk, nbeg, nend);
-      }
+      __syncthreads();
       // ---- 3. the runs
       float* pm    = P.piece_mom + (std::size_t)piece * kMomStride;
       float  s0run = 0.0f;
@@ -977,7 +1007,10 @@ namespace rgc {
           if (ds[g] != 0.0f) {
             const float s2 = acc[0][g] + acc[1][g];
             const float v  = ((rtype >> g) & 1u) ? s0run - s2 : s2;
-            atomicAdd(&prow[(ch.x + g) * 32 + lane], (double)ds[g] * (double)v);
+            // RED (no return value: nothing waits for the L2 round trip)
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(prow + (ch.x + g) * 32 + lane),
+                         "d"((double)ds[g] * (double)v)
+                         : "memory");
           }
         }
       };
@@ -1010,8 +1043,10 @@ namespace rgc {
           }
         }
       };
+      // warp w streams run w (warp 0 also run 8: with the phase shift runs 0 and 8 are the two
+      // parts of one eighth)
 #pragma unroll 1
-      for (int r = 0; r < kSub; ++r) {
+      for (int r = warp; r < kSub; r += kPWarps) {
         const int2 rt = runtab[r];
         if (rt.y == 0) {
           if (lane < 2) {
@@ -1029,29 +1064,12 @@ namespace rgc {
           do_chunks(r - 1, false, r, rb, n4, rt.y); // a threshold of sub-bucket r - 1 strays up here
         }
       }
-      __syncwarp(); // every lane is done with B before the next piece's scatter
-      piece = npiece;
-      b     = nbk;
-      beg   = nbeg;
-      end   = nend;
     }
     if (lane == 0 && lane_evals != 0ull) {
       atomicAdd(P.lane_evals, lane_evals);
     }
-    // ---- the CTA's eight warp rows -> one row, in warp order (the reductions above were
-    // performed at L2; the loads below bypass L1)
-    __threadfence();
-    __syncthreads();
-    const double* rows = P.partials + (std::size_t)blockIdx.x * kPWarps * P.nslots;
-    for (int j = tid; j < P.nslots; j += kPThreads) {
-      double s = 0.0;
-#pragma unroll
-      for (int w = 0; w < kPWarps; ++w) {
-        s += __ldcg(rows + (std::size_t)w * P.nslots + j);
-      }
-      P.cta_partials[(std::size_t)blockIdx.x * P.nslots + j] = s;
-    }
   }
+
   // msum[b * (kSub + 1) + a] = {sum_{s >= a} S0_{b,s}, sum_{s >= a} S1_{b,s}}: suffix sums over the
   // sub-buckets of bucket b (a = 0: the whole bucket, a = kSub: 0) of the fp64 sums over the
   // bucket's pieces, lane-strided then a fixed shuffle tree.  Also counts (roofline accounting,
@@ -1062,20 +1080,19 @@ namespace rgc {
                         double2* __restrict__ msum, const int2* __restrict__ slot_i,
                         const int* __restrict__ bin_of_slot, const float4* __restrict__ coef_dh,
                         int nslots, unsigned long long* __restrict__ ontable) {
-    __shared__ int bstart[kPMaxBuckets + 2], pstart[kPMaxBuckets + 2], tmp[2 * kPWarps];
+    __shared__ int    bstart[kPMaxBuckets + 2], pstart[kPMaxBuckets + 2], tmp[2 * kPWarps];
+    __shared__ double red[kPWarps][2 * kSub];
+    __shared__ int    red_live[kPWarps];
     block_scan_buckets(tot, nb, bstart, pstart, tmp);
-    const int lane = threadIdx.x & 31;
-    const int b    = blockIdx.x * kPWarps + (threadIdx.x >> 5);
-    if (b >= nb) {
-      return;
-    }
-    double s0[kSub], s1[kSub];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b   = blockIdx.x; // one CTA per bucket
+    double    s0[kSub], s1[kSub];
 #pragma unroll
     for (int s = 0; s < kSub; ++s) {
       s0[s] = 0.0;
       s1[s] = 0.0;
     }
-    for (int p = pstart[b] + lane; p < pstart[b + 1]; p += 32) {
+    for (int p = pstart[b] + tid; p < pstart[b + 1]; p += kPThreads) {
       const float4* m4 = reinterpret_cast<const float4*>(piece_mom + (std::size_t)p * kMomStride);
 #pragma unroll
       for (int h = 0; h < kMomStride / 4; ++h) {
@@ -1089,7 +1106,7 @@ namespace rgc {
       }
     }
     int live = 0;
-    for (int sl = lane; sl < nslots; sl += 32) {
+    for (int sl = tid; sl < nslots; sl += kPThreads) {
       live += (bin_of_slot[sl] >= 0 && coef_dh[max(slot_i[sl].x + b, 0)].x != 0.0f) ? 1 : 0;
     }
 #pragma unroll
@@ -1102,17 +1119,31 @@ namespace rgc {
       live += __shfl_xor_sync(0xffffffffu, live, off);
     }
     if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < kSub; ++s) {
+        red[warp][2 * s]     = s0[s];
+        red[warp][2 * s + 1] = s1[s];
+      }
+      red_live[warp] = live;
+    }
+    __syncthreads();
+    if (tid == 0) {
       double2* out = msum + (std::size_t)b * (kSub + 1);
       double   a0 = 0.0, a1 = 0.0;
       out[kSub]   = make_double2(0.0, 0.0);
-#pragma unroll
       for (int s = kSub - 1; s >= 0; --s) {
-        a0 += s0[s];
-        a1 += s1[s];
+        for (int w = 0; w < kPWarps; ++w) { // fixed order
+          a0 += red[w][2 * s];
+          a1 += red[w][2 * s + 1];
+        }
         out[s] = make_double2(a0, a1);
       }
-      if (tot[b] != 0 && live != 0) {
-        atomicAdd(ontable, (unsigned long long)tot[b] * (unsigned long long)live);
+      int lv = 0;
+      for (int w = 0; w < kPWarps; ++w) {
+        lv += red_live[w];
+      }
+      if (tot[b] != 0 && lv != 0) {
+        atomicAdd(ontable, (unsigned long long)tot[b] * (unsigned long long)lv);
       }
     }
   }
@@ -1636,9 +1667,8 @@ namespace rgc {
     auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
     const std::size_t off_msum = 0;
     const std::size_t off_out  = align(off_msum + (std::size_t)pp.nb * (kSub + 1) * sizeof(double2));
-    const std::size_t off_cpart = align(off_out + pp.nslots * sizeof(double));
-    const std::size_t off_part = align(off_cpart + (std::size_t)pair_ctas * pp.nslots * sizeof(double));
-    const std::size_t part_bytes = (std::size_t)pair_ctas * kPWarps * pp.nslots * sizeof(double);
+    const std::size_t off_part = align(off_out + pp.nslots * sizeof(double));
+    const std::size_t part_bytes = (std::size_t)pair_ctas * pp.nslots * sizeof(double);
     const std::size_t off_tot  = align(off_part + part_bytes);
     const std::size_t off_cnt  = align(off_tot + (std::size_t)pp.nbp * sizeof(int));
     const std::size_t off_mom  = align(off_cnt + (std::size_t)pp.nbp * rows0 * sizeof(int));
@@ -1689,11 +1719,10 @@ namespace rgc {
     P.sorted    = reinterpret_cast<float2*>(sb + off_sort);
     P.piece_mom = reinterpret_cast<float*>(sb + off_mom);
     P.partials  = reinterpret_cast<double*>(sb + off_part);
-    P.cta_partials = reinterpret_cast<double*>(sb + off_cpart);
     P.nslots    = pp.nslots;
     P.o_coef = (int)L.coef; P.o_bstart = (int)L.bstart; P.o_pstart = (int)L.pstart;
     P.o_tmp = (int)L.tmp; P.o_slot = (int)L.slot; P.o_chunk = (int)L.chunk;
-    P.o_warp = (int)L.warp; P.warp_stride = (int)L.warp_stride;
+    P.o_sorted = (int)L.sorted; P.o_cur = (int)L.cur; P.o_wtot = (int)L.wtot; P.o_run = (int)L.run;
     double2* d_msum = reinterpret_cast<double2*>(sb + off_msum);
     RGC_CUDA(cudaFuncSetAttribute(sync_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RGC_CUDA(cudaFuncSetAttribute(sync_pair_kernel<kPMaxGPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1745,12 +1774,12 @@ namespace rgc {
       }
       RGC_CUDA(cudaGetLastError());
       RGC_CUDA(cudaEventRecord(c.ev[4], c.stream));
-      pair_moments_kernel<<<(pp.nb + kPWarps - 1) / kPWarps, kPThreads, 0, c.stream>>>(
+      pair_moments_kernel<<<pp.nb, kPThreads, 0, c.stream>>>(
         P.tot, pp.nb, P.piece_mom, d_msum, P.slot_i, reinterpret_cast<const int*>(cp->dev + cp->off_map),
         P.coef_dh, pp.nslots, P.lane_evals + 1);
       RGC_CUDA(cudaGetLastError());
       pair_final_kernel<<<(pp.nslots + kPWarps - 1) / kPWarps, kPThreads, 0, c.stream>>>(
-        P.cta_partials, pair_ctas, pp.nslots, P.slot_i, P.slot_f,
+        P.partials, pair_ctas, pp.nslots, P.slot_i, P.slot_f,
         reinterpret_cast<const int*>(cp->dev + cp->off_sub), P.extmask, P.coef_dh,
         reinterpret_cast<const double2*>(cp->dev + cp->off_vs), d_msum, pp.nb, d_out);
       RGC_CUDA(cudaGetLastError());
