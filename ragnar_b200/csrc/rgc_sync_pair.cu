@@ -1,5 +1,5 @@
-// Bucketed hinge form of the particle synchrotron spectrum for sm_100a — the
-// FP32-pipe-bound main path of SynchrotronSpectrum_<D>D.
+// Bucketed hinge form of the particle synchrotron spectrum for sm_100a — the main path
+// of SynchrotronSpectrum_<D>D.
 //
 // Replaces (reference paths relative to haykh/ragnar @ fceb6b08):
 //   sync::Kernel<D>::operator() / OmegaSync_ChiR   src/physics/synchrotron.hpp:145-232
@@ -14,13 +14,26 @@
 //     F = v_q + s_q * u + (s_{q+1} - s_q) * max(0, u - h_q)
 // (h_q ~ 1 is the position of the table node between the two cells).  Summed
 // over the bucket's particles with weights w_i = chiR_i:
-//     sum_i w_i F_ij = v_q S0 + s_q (fa_j S0 + S1) + ds_q * sum_i w_i max(0, fa_j - h_q + fc_i)
-// S0 = sum w_i and S1 = sum w_i fc_i do not depend on the bin; only the hinge
-// needs per-pair work:  r = sat(fa'_j + fc_i);  S2_j += w_i * r   — one FFMA.SAT
-// and one FFMA per (particle, bin) evaluation, nothing else in the inner loop.
-// (The upper clamp of .SAT never binds for real bins: fa' + fc < 1 + |h - 1|.)
-// Two spare lanes per warp column run the same instructions with fa' = 1 and
-// fa' = 0 and so deliver S0 and S1 for free.
+//     sum_i w_i F_ij = v_q S0 + s_q (fa_j S0 + S1) + ds_q * sum_i w_i max(0, fc_i + fa'_j),
+// fa'_j = fa_j - h_q.  S0 = sum w_i and S1 = sum w_i fc_i do not depend on the bin; only
+// the hinge needs per-pair work:  r = sat(fc_i + fa'_j);  S2_j += w_i * r   (FADD.SAT +
+// FFMA).
+//
+// Sub-bucket decomposition (round 2).  The hinge of bin j is identically 0 for every
+// particle with fc <= -fa'_j and LINEAR in fc for every particle above.  Cut the bucket
+// into sub-buckets by s = floor(8 fc + phi): a sub-bucket that lies entirely below the
+// bin's threshold contributes nothing, one that lies entirely above contributes
+// S1_s + fa'_j S0_s (its own moments), and only the ONE sub-bucket that contains the
+// threshold needs the pair loop — about one pair in eight.  Bins are therefore grouped
+// into 32-lane groups by the sub-bucket of their threshold, a piece of the sorted array is
+// counting-sorted by sub-bucket, and run s is streamed through the groups of sub-bucket s
+// only; pair_final_kernel adds the moment part from suffix sums over the sub-buckets.
+// The phase phi puts the sub-bucket boundaries into the widest gap between the bins'
+// thresholds (commensurate grids put every threshold ON a multiple of 1/8); where a float
+// threshold still strays across a boundary with the table nodes' 1e-5 wiggle, the plan
+// makes that sub-bucket's groups see the neighbouring run too (per bucket, `extmask`).
+// The first two lanes of every sub-bucket's first group carry fa' = 1 and fa' = 0 and so
+// deliver the run's S0 and S1 from the same two instructions.
 //
 // Pipeline (one pass per <= 2^27 particles), all on the compute stream:
 //   1 sync_prologue_kernel  HBM-bound (36 B read, 10 B written per particle):
@@ -32,30 +45,33 @@
 //       bucket + bucket totals (one warp per bucket)
 //   3 sync_sort_kernel      HBM-bound (10 B read, 8 B written): a CTA walks its row
 //       tile by tile: TMA bulk copy of the tile's (fc, w, key) into shared memory,
-//       warp-synchronous stable ranking (ballot match), scan, scatter to bucket
-//       order INSIDE shared memory, then coalesced write-out of every bucket run to
-//       its place in the GLOBAL bucket order (scattered 8-byte global stores cost
-//       ~5 clk each per SM; runs of a tile are contiguous).  Row order x tile order
-//       x (warp, step, lane) order: deterministic.
-//   4 sync_pair_kernel      FP32-bound: the sorted array is cut into pieces of
-//       <= 1024 entries of one bucket; a warp takes pieces round-robin, loads the
-//       (ds, h) of its lanes' cells once per piece and streams the piece through a
-//       warp-private ring of TMA bulk copies (4 x 512 B, mbarrier per stage) into
-//       the 2-instruction pair loop fed by broadcast LDS.128.  No CTA barrier
-//       inside the loop.
-//   5 pair_moments_kernel / pair_final_kernel   fp64 bucket moments from the
-//       pieces' spare-lane sums, CTA partials + the linear part
-//       v_q S0 + s_q (fa_j S0 + S1)  ->  one value per bin.
-// Hinge sums are float per piece, folded into fp64 per piece; every reduction
-// runs in a fixed order: bitwise reproducible.
+//       ranking, scan, scatter to bucket order INSIDE shared memory, then coalesced
+//       write-out of every bucket run to its place in the GLOBAL bucket order
+//       (scattered 8-byte global stores cost ~5 clk each per SM; runs of a tile are
+//       contiguous).  Row order x tile order x (warp, step, lane) order: deterministic.
+//   4 sync_pair_kernel      a CTA takes pieces of <= 4096 sorted entries of one bucket:
+//       16 coalesced loads per thread, CTA-wide counting sort by sub-bucket in shared
+//       memory ((thread, entry) order, no atomics), then warp w streams run w through
+//       its lane groups with the roles swapped — a lane owns every 32nd particle of
+//       the run and keeps the partial sums of the group's 32 bins in registers, a
+//       butterfly transpose-reduction leaves bin j's total in lane j — and adds
+//       ds_q * sum (fp64) into the CTA's row of partial sums with RED.ADD.F64
+//       (a slot is only ever touched by one warp of the CTA: fixed order).
+//   5 pair_moments_kernel / pair_final_kernel   fp64 sub-bucket moments (suffix sums)
+//       from the runs' moment lanes; CTA partials + the linear part
+//       v_q S0 + s_q (fa_j S0 + S1) + the hinge of the sub-buckets beyond the
+//       threshold  ->  one value per bin.
+// Hinge sums are float per run (<= 4096 / 32 terms per lane, then a 32-lane tree), folded
+// into fp64 per run; every reduction runs in a fixed order: bitwise reproducible.
 //
 // Requires a table with F = 0 at both ends (true for sync::TabulateFfunc, whose
 // first node is forced to 0 and whose nodes beyond x = 20 are 0); any other table,
 // very wide bin ranges and the FromDist form use the gather kernel.
 //
-// Roofline: 2 FP32-pipe instructions per evaluation against the measured FFMA issue
-// rate (rgc_measure_peak kind 0/1); HBM: 64 B per particle over the three streaming
-// kernels, amortised over nbins.
+// Roofline: the pipeline is HBM-bound (64 B per particle over the three streaming
+// kernels + 8 B read by the pair kernel); the pair loop issues about particles x 32 lanes
+// x groups-per-sub-bucket evaluations (2 FP32-pipe instructions each) instead of
+// particles x bins.
 //
 // Compiled with -fmad=false: every FMA below is an explicit fmaf()/fma().
 #include "rgc_internal.hpp"
@@ -138,7 +154,7 @@ namespace rgc {
     std::size_t coef, bstart, pstart, tmp, slot, chunk, sorted, cur, wtot, run, total;
   };
   // shared memory of the pair kernel: plan tables, the piece sorted by sub-bucket (every run
-  // padded to a multiple of 8 entries), the per-thread cursors of the sort, packed warp totals,
+  // padded to a multiple of 16 entries), the per-thread cursors of the sort, packed warp totals,
   // the run table
   __host__ __device__ inline PairSmem pair_smem_layout(int n_pad, int nbp, int nslots, int nchunks) {
     PairSmem L;
@@ -153,7 +169,7 @@ namespace rgc {
     L.run = o;     o = pair_align16(o + (std::size_t)kSub * sizeof(int2));
     L.cur = o;     o = pair_align16(o + (std::size_t)kSub * kPThreads * sizeof(int));
     o = (o + 127) & ~std::size_t(127);
-    L.sorted = o;  o = o + (std::size_t)(kPieceLen + 8 * kSub) * sizeof(float2);
+    L.sorted = o;  o = o + (std::size_t)(kPieceLen + 64 * kSub) * sizeof(float2);
     L.total  = o;
     return L;
   }
@@ -789,8 +805,7 @@ namespace rgc {
   // lanes run the same two instructions on sat(fc + fa0) and the run's S0 lane gives
   // S0 - sum w sat(u), which is exactly 0 when every particle of the run is beyond the
   // tail (both lanes then execute the identical float sequence).
-  template <int MAXNA>
-  __global__ void __launch_bounds__(kPThreads, MAXNA <= 2 ? 3 : 2)
+  __global__ void __launch_bounds__(kPThreads, 2)
     sync_pair_kernel(const __grid_constant__ PairParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* coef     = reinterpret_cast<float4*>(smem_raw + P.o_coef);
@@ -819,31 +834,28 @@ namespace rgc {
     }
     block_scan_buckets(P.tot, nb, bstart, pstart, tmp); // ends with __syncthreads()
 
+    // sub-bucket of a fraction fc in [0, 1]: floor(8 fc + phi) as the round-to-nearest of
+    // 8 fc + (phi - 1/2), taken from the mantissa after adding 1.5 * 2^23 (no F2I on the XU
+    // pipe; phi < 1 keeps the result <= 8; a tie lies within the plan's eps of a boundary, where
+    // either side is valid)
+    const float sub_bias = P.sub_phi - 0.5f;
+    auto sub_of = [&](float fc) {
+      return __float_as_int(fmaf(fc, (float)kSubDiv, sub_bias) + 12582912.0f) & 15;
+    };
     const int npieces = pstart[nb];
     double*   prow    = P.partials + (std::size_t)blockIdx.x * P.nslots;
     unsigned long long lane_evals = 0; // hinge evaluations issued by this warp
-    // bucket and sorted range of a piece: first b with pstart[b + 1] > piece
-    auto locate = [&](int piece, int& b, int& beg, int& end) {
-      int lo = 0, hi = nb - 1;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (pstart[mid + 1] <= piece) {
-          lo = mid + 1;
-        } else {
-          hi = mid;
-        }
-      }
-      b   = lo;
-      beg = bstart[lo] + (piece - pstart[lo]) * kPieceLen;
-      end = min(beg + kPieceLen, bstart[lo + 1]);
-    };
-
+    int bcur = 0; // the CTA's pieces ascend: the bucket search resumes where it stopped
     for (int piece = blockIdx.x; piece < npieces; piece += gridDim.x) {
-      int b, beg, end;
-      locate(piece, b, beg, end);
-      const int n = end - beg; // even, <= kPieceLen
+      while (pstart[bcur + 1] <= piece) {
+        ++bcur;
+      }
+      const int b   = bcur;
+      const int beg = bstart[b] + (piece - pstart[b]) * kPieceLen;
+      const int n   = min(kPieceLen, bstart[b + 1] - beg); // even
       // ---- 1. the piece: 16 coalesced 8-byte loads per thread, all in flight at once (entries
       // beyond a short piece become zero-weight pads); the bucket's chunk table rides along
+      // (used by the runs: those loads complete underneath the sort)
       float2        ent[kPieceEnt];
       const float2* src = P.sorted + beg;
 #pragma unroll
@@ -860,11 +872,13 @@ namespace rgc {
       }
       // ---- 2. counting sort of the piece by sub-bucket, in (thread, entry) order: per-thread
       // 5-bit counters of the 9 sub-buckets packed into one 64-bit register, warp scans of the
-      // counters packed two to a register, warp totals through shared memory
+      // counters packed two to a register, warp totals through shared memory.  Two CTA barriers
+      // per piece: every warp has left the previous piece's runs when the first one opens, and
+      // nothing that the runs read is written before it.
       unsigned long long cnt = 0ull;
 #pragma unroll
       for (int st = 0; st < kPieceEnt; ++st) {
-        const int s = min(kSub - 1, (int)fmaf(ent[st].x, (float)kSubDiv, P.sub_phi));
+        const int s = sub_of(ent[st].x);
         cnt += 1ull << (5 * s);
       }
       unsigned pk[kSubPk], incl[kSubPk];
@@ -885,7 +899,6 @@ namespace rgc {
           }
         }
       }
-      __syncthreads(); // the previous piece's runs are done: B, cur, wtot, runtab are free
       if (lane == 31) {
 #pragma unroll
         for (int j = 0; j < kSubPk; ++j) {
@@ -893,20 +906,21 @@ namespace rgc {
         }
       }
       __syncthreads();
-      if (warp == 0) {
-        // exclusive prefix over the warps (packed), totals, padded run starts
-        unsigned tot_pk = 0u;
-        if (lane < kSubPk) {
+      // every warp for itself: (packed) prefix over the warps before it, totals, padded run starts
+      unsigned pre_pk = 0u, tot_pk = 0u;
+      if (lane < kSubPk) {
 #pragma unroll
-          for (int w = 0; w < kPWarps; ++w) {
-            const unsigned t         = wtot[w * kSubPk + lane];
-            wtot[w * kSubPk + lane]  = tot_pk;
-            tot_pk += t;
-          }
+        for (int w = 0; w < kPWarps; ++w) {
+          const unsigned t = wtot[w * kSubPk + lane];
+          pre_pk += w < warp ? t : 0u;
+          tot_pk += t;
         }
+      }
+      int start_k; // lane k: first sorted entry of run k
+      {
         const unsigned tp  = __shfl_sync(0xffffffffu, tot_pk, lane >> 1);
         const int      tot = lane < kSub ? (int)((tp >> ((lane & 1) * 16)) & 0xffffu) : 0;
-        const int      pad = (tot + 7) & ~7; // whole groups of 4 float4
+        const int      pad = (tot + 63) & ~63; // two particles per lane and loop iteration
         int            inc = pad;
 #pragma unroll
         for (int off = 1; off < 16; off <<= 1) {
@@ -915,27 +929,27 @@ namespace rgc {
             inc += t;
           }
         }
-        if (lane < kSub) {
-          const int start = inc - pad;
-          runtab[lane]    = make_int2(start, pad);
+        start_k = inc - pad;
+        if (warp == 0 && lane < kSub) {
+          runtab[lane] = make_int2(start_k, pad);
           for (int i = tot; i < pad; ++i) {
-            B[start + i] = make_float2(0.0f, 0.0f); // zero-weight pad
+            B[start_k + i] = make_float2(0.0f, 0.0f); // zero-weight pad
           }
         }
       }
-      __syncthreads();
 #pragma unroll
       for (int k = 0; k < kSub; ++k) {
-        const unsigned sh = (k & 1) * 16;
-        const int base = runtab[k].x + (int)((wtot[warp * kSubPk + (k >> 1)] >> sh) & 0xffffu) +
-                         (int)(((incl[k >> 1] - pk[k >> 1]) >> sh) & 0xffffu);
-        cur[k * kPThreads + tid] = base;
+        const unsigned sh   = (k & 1) * 16;
+        const int      st_k = __shfl_sync(0xffffffffu, start_k, k);
+        const unsigned pr   = __shfl_sync(0xffffffffu, pre_pk, k >> 1);
+        cur[k * kPThreads + tid] =
+          st_k + (int)((pr >> sh) & 0xffffu) + (int)(((incl[k >> 1] - pk[k >> 1]) >> sh) & 0xffffu);
       }
       {
         unsigned long long seen = 0ull;
 #pragma unroll
         for (int st = 0; st < kPieceEnt; ++st) {
-          const int s    = min(kSub - 1, (int)fmaf(ent[st].x, (float)kSubDiv, P.sub_phi));
+          const int s    = sub_of(ent[st].x);
           const int rank = (int)((seen >> (5 * s)) & 31ull);
           seen += 1ull << (5 * s);
           B[cur[s * kPThreads + tid] + rank] = ent[st];
@@ -945,101 +959,91 @@ namespace rgc {
       // ---- 3. the runs
       float* pm    = P.piece_mom + (std::size_t)piece * kMomStride;
       float  s0run = 0.0f;
-      // one chunk (<= kPMaxGPW lane groups, the first NA of them on the table for this bucket)
-      // over the run [rb, rb + n4): r = sat(fc + fa'), acc += w r.  Two accumulator chains per
-      // group, the same for every NA: the zero-tail lanes rely on identical float sequences.
-      auto run_chunk = [&](auto na_tag, const int4 ch, const bool own, const int r,
-                           const float4* __restrict__ rb, const int n4) {
-        constexpr int NA = decltype(na_tag)::value;
-        float    fap[NA], ds[NA], acc[2][NA];
-        unsigned rtype = 0;
+      // One lane group (32 bins, lane = bin in the slot tables) over the run [re, re + len), with
+      // the roles swapped for the loop: a lane owns every 32nd PARTICLE of the run and keeps the
+      // partial sums of all 32 bins in registers (the 32 fa' are warp-uniform register copies), so
+      // the loop is r = sat(fc + fa'_j), acc_j += w r for j = 0..31 per particle with no shared
+      // memory traffic beyond one coalesced 8-byte load per particle (a broadcast load per
+      // particle made the lanes = bins form shared-memory bound at one lane group: 1 wavefront
+      // per 2 instructions).  A butterfly transpose-reduction then leaves bin j's total in lane j.
+      // The same instruction sequence and the same reduction tree serve every bin, so the zero-tail
+      // bins (S0 - sum w sat(u)) are exactly 0 when every particle of the run is beyond the tail.
+      auto run_group = [&](const int group, const bool moments, const int r,
+                           const float2* __restrict__ re, const int len) {
+        const int2   sl    = slot_tab[group * 32 + lane];
+        const float  fa0   = __int_as_float(sl.y);
+        const float4 dh    = coef[max(sl.x + b, 0)];
+        const bool   spare = sl.x < 0;              // moment lanes and unused lanes
+        const bool   tail  = !spare && dh.z < 0.0f; // cell pair next to the zero tail
+        const float  fap   = spare ? fa0 - 1.0f : (tail ? fa0 : fa0 - dh.y);
+        const float  ds    = spare ? 0.0f : dh.x;
+        float f[32], acc[32];
 #pragma unroll
-        for (int g = 0; g < NA; ++g) {
-          const int2   sl    = slot_tab[(ch.x + g) * 32 + lane];
-          const float  fa0   = __int_as_float(sl.y);
-          const float4 dh    = coef[max(sl.x + b, 0)];
-          const bool   spare = sl.x < 0;              // moment lanes and unused lanes
-          const bool   tail  = !spare && dh.z < 0.0f; // cell pair next to the zero tail
-          fap[g]    = spare ? fa0 - 1.0f : (tail ? fa0 : fa0 - dh.y);
-          ds[g]     = spare ? 0.0f : dh.x;
-          rtype |= tail ? (1u << g) : 0u;
-          acc[0][g] = 0.0f;
-          acc[1][g] = 0.0f;
+        for (int j = 0; j < 32; ++j) {
+          f[j]   = __shfl_sync(0xffffffffu, fap, j);
+          acc[j] = 0.0f;
         }
-#define RGC_PAIR_ONE(FC, W, SET)                                                              \
-  {                                                                                           \
-    float rr[NA];                                                                             \
-    _Pragma("unroll") for (int g = 0; g < NA; ++g) { rr[g] = __saturatef((FC) + fap[g]); }    \
-    _Pragma("unroll") for (int g = 0; g < NA; ++g) { acc[SET][g] = fmaf((W), rr[g], acc[SET][g]); } \
-  }
-#define RGC_PAIR_BODY(Q) RGC_PAIR_ONE((Q).x, (Q).y, 0) RGC_PAIR_ONE((Q).z, (Q).w, 1)
-        // runs are padded to whole groups of 4 float4 (8 entries); the loads of the next two
-        // float4 are in flight while the current two are consumed (ping-pong registers)
-        float4 q0 = rb[0], q1 = rb[1];
+        // runs are padded to a multiple of 64 entries: two particles per lane and iteration, the
+        // next two in flight
+        float2 p0 = re[lane], p1 = re[32 + lane];
 #pragma unroll 1
-        for (int p = 0; p < n4 - 4; p += 4) {
-          const float4 a0 = rb[p + 2], a1 = rb[p + 3];
-          RGC_PAIR_BODY(q0)
-          RGC_PAIR_BODY(q1)
-          q0 = rb[p + 4];
-          q1 = rb[p + 5];
-          RGC_PAIR_BODY(a0)
-          RGC_PAIR_BODY(a1)
-        }
-        {
-          const float4 a0 = rb[n4 - 2], a1 = rb[n4 - 1];
-          RGC_PAIR_BODY(q0)
-          RGC_PAIR_BODY(q1)
-          RGC_PAIR_BODY(a0)
-          RGC_PAIR_BODY(a1)
-        }
-#undef RGC_PAIR_BODY
-#undef RGC_PAIR_ONE
-        const float m0 = acc[0][0] + acc[1][0];
-        if (own && ch.z != 0) {
-          s0run = __shfl_sync(0xffffffffu, m0, 0);
-          if (lane < 2) {
-            pm[r * 2 + lane] = m0; // lanes 0 / 1 of group 0: S0 / S1 of the run
+        for (int e = 64; e < len; e += 64) {
+          const float2 n0 = re[e + lane], n1 = re[e + 32 + lane];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            acc[j] = fmaf(p0.y, __saturatef(p0.x + f[j]), acc[j]);
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            acc[j] = fmaf(p1.y, __saturatef(p1.x + f[j]), acc[j]);
+          }
+          p0 = n0;
+          p1 = n1;
         }
 #pragma unroll
-        for (int g = 0; g < NA; ++g) {
-          if (ds[g] != 0.0f) {
-            const float s2 = acc[0][g] + acc[1][g];
-            const float v  = ((rtype >> g) & 1u) ? s0run - s2 : s2;
-            // RED (no return value: nothing waits for the L2 round trip)
-            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(prow + (ch.x + g) * 32 + lane),
-                         "d"((double)ds[g] * (double)v)
-                         : "memory");
+        for (int j = 0; j < 32; ++j) {
+          acc[j] = fmaf(p0.y, __saturatef(p0.x + f[j]), acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          acc[j] = fmaf(p1.y, __saturatef(p1.x + f[j]), acc[j]);
+        }
+        // transpose-reduce: after the stage with partner lane ^ off a lane keeps the half of its
+        // values whose bin index has that bit equal to its own; lane j ends with bin j
+#pragma unroll
+        for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < n / 2; ++i) {
+            const float send = upper ? acc[i] : acc[i + n / 2];
+            const float keep = upper ? acc[i + n / 2] : acc[i];
+            acc[i]           = keep + __shfl_xor_sync(0xffffffffu, send, off);
           }
+        }
+        const float s2 = acc[0];
+        if (moments) {
+          s0run = __shfl_sync(0xffffffffu, s2, 0);
+          if (lane < 2) {
+            pm[r * 2 + lane] = s2; // lanes 0 / 1 of the sub-bucket's first group: S0 / S1 of the run
+          }
+        }
+        if (ds != 0.0f) {
+          const float v = tail ? s0run - s2 : s2;
+          // RED (no return value: nothing waits for the L2 round trip)
+          asm volatile("red.global.add.f64 [%0], %1;" ::"l"(prow + group * 32 + lane),
+                       "d"((double)ds * (double)v)
+                       : "memory");
         }
       };
-      auto do_chunks = [&](const int sub, const bool own, const int r, const float4* rb, const int n4,
-                           const int len) {
+      auto do_chunks = [&](const int sub, const bool own, const int r, const float2* re, const int len) {
         for (int c = P.chunk_first[sub]; c < P.chunk_first[sub + 1]; ++c) {
-          const int4 ch = chunks[c];
+          const int4     ch  = chunks[c];
           const unsigned nav = c < 32 ? na_reg[0] : (c < 64 ? na_reg[1] : na_reg[2]);
           const int      na  = P.force_groups != 0u ? ch.y : (int)__shfl_sync(0xffffffffu, nav, c & 31);
-          if (na == 0) {
-            continue; // none of these bins is on the table for this bucket
-          }
+          // the first na lane groups of the chunk are on the table for this bucket
           lane_evals += (unsigned long long)len * (unsigned)(na * 32);
-          switch (na) {
-#define RGC_NA_CASE(N)                                                        \
-  case N:                                                                     \
-    if constexpr (N <= MAXNA) {                                               \
-      run_chunk(std::integral_constant<int, N> {}, ch, own, r, rb, n4);       \
-    }                                                                         \
-    break;
-            RGC_NA_CASE(1)
-            RGC_NA_CASE(2)
-            RGC_NA_CASE(3)
-            RGC_NA_CASE(4)
-            RGC_NA_CASE(5)
-            RGC_NA_CASE(6)
-            RGC_NA_CASE(7)
-            RGC_NA_CASE(8)
-#undef RGC_NA_CASE
+          for (int g = 0; g < na; ++g) {
+            run_group(ch.x + g, own && ch.z != 0 && g == 0, r, re, len);
           }
         }
       };
@@ -1054,14 +1058,13 @@ namespace rgc {
           }
           continue;
         }
-        const float4* rb = reinterpret_cast<const float4*>(B + rt.x);
-        const int     n4 = rt.y >> 1; // float4 = 2 entries
-        do_chunks(r, true, r, rb, n4, rt.y); // the sub-bucket's own bins (first chunk: moment lanes)
+        const float2* re = B + rt.x;
+        do_chunks(r, true, r, re, rt.y); // the sub-bucket's own bins (first group: moment lanes)
         if (r + 1 < kSub && ((em >> (r + 1)) & 1u)) {
-          do_chunks(r + 1, false, r, rb, n4, rt.y); // a threshold of sub-bucket r + 1 strays down here
+          do_chunks(r + 1, false, r, re, rt.y); // a threshold of sub-bucket r + 1 strays down here
         }
         if (r > 0 && ((em >> (kSub + r - 1)) & 1u)) {
-          do_chunks(r - 1, false, r, rb, n4, rt.y); // a threshold of sub-bucket r - 1 strays up here
+          do_chunks(r - 1, false, r, re, rt.y); // a threshold of sub-bucket r - 1 strays up here
         }
       }
     }
@@ -1656,13 +1659,7 @@ namespace rgc {
     const Geom        g0    = geom_for(cnt0);
     const int         rows0 = g0.rows;
     const std::size_t npad0 = (std::size_t)g0.ntiles * kPTile;
-    int max_groups = 1;
-    for (const int4& ch : pp.chunks) {
-      max_groups = std::max(max_groups, ch.y);
-    }
-    const bool small_na = max_groups <= 2; // the 3-CTA-per-SM instantiation
-    const int  pair_ctas_per_sm = (small_na && 3 * (smem + 1024) <= 227 * 1024) ? 3 : 2;
-    const int  pair_ctas        = c.sm_count * pair_ctas_per_sm;
+    const int  pair_ctas = c.sm_count * 2;
     const std::size_t max_pieces  = cnt0 / kPieceLen + (std::size_t)pp.nbp + 2;
     auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
     const std::size_t off_msum = 0;
@@ -1724,9 +1721,7 @@ namespace rgc {
     P.o_tmp = (int)L.tmp; P.o_slot = (int)L.slot; P.o_chunk = (int)L.chunk;
     P.o_sorted = (int)L.sorted; P.o_cur = (int)L.cur; P.o_wtot = (int)L.wtot; P.o_run = (int)L.run;
     double2* d_msum = reinterpret_cast<double2*>(sb + off_msum);
-    RGC_CUDA(cudaFuncSetAttribute(sync_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RGC_CUDA(cudaFuncSetAttribute(sync_pair_kernel<kPMaxGPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+    RGC_CUDA(cudaFuncSetAttribute(sync_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     double* d_out  = reinterpret_cast<double*>(sb + off_out);
     float               pro_ms = 0.f, sort_ms = 0.f;
     const std::size_t   sort_smem = sort_smem_layout(pp.nbp).total;
@@ -1767,11 +1762,7 @@ namespace rgc {
       RGC_CUDA(cudaGetLastError());
       RGC_CUDA(cudaEventRecord(c.ev[5], c.stream));
       RGC_CUDA(cudaMemsetAsync(P.partials, 0, part_bytes, c.stream));
-      if (small_na) {
-        sync_pair_kernel<2><<<pair_ctas, kPThreads, smem, c.stream>>>(P);
-      } else {
-        sync_pair_kernel<kPMaxGPW><<<pair_ctas, kPThreads, smem, c.stream>>>(P);
-      }
+      sync_pair_kernel<<<pair_ctas, kPThreads, smem, c.stream>>>(P);
       RGC_CUDA(cudaGetLastError());
       RGC_CUDA(cudaEventRecord(c.ev[4], c.stream));
       pair_moments_kernel<<<pp.nb, kPThreads, 0, c.stream>>>(
