@@ -80,6 +80,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <type_traits>
 #include <vector>
 
@@ -98,8 +99,15 @@ namespace rgc {
   constexpr unsigned kInvalidKey = 0xffffu;
   constexpr int kPTile       = 4096; // particles per tile of the prologue / sort kernels
   constexpr int kPSteps      = kPTile / kPThreads;
-  constexpr int kPieceLen    = 4096; // sorted entries per work unit (one CTA) of the pair kernel
-  constexpr int kPieceEnt    = kPieceLen / kPThreads; // entries per thread in the piece's sub-sort
+  constexpr int kPieceLen    = 4096; // sorted entries per work unit of the pair kernel
+  // the pair kernel's CTA: 8 run warps + two sort groups of 4 warps
+  constexpr int kPairRunThreads = 256;
+  constexpr int kPairSortGroup  = 128;
+  constexpr int kPairSortWarps  = kPairSortGroup / 32;
+  constexpr int kPairThreads    = kPairRunThreads + 2 * kPairSortGroup;
+  constexpr int kPairSortEnt    = kPieceLen / kPairSortGroup; // entries per sort thread
+  constexpr int kPairBufLen     = kPieceLen + 64 * kSub; // a sorted piece, every run padded to 64 entries
+  constexpr int kPairBufs       = 4; // sorted pieces in flight: each sort group works up to two pieces ahead
 
   // fp64 constants of the prologue, read as constant-bank operands (an immediate double
   // whose low word is not zero costs two UMOVs per use otherwise)
@@ -162,14 +170,14 @@ namespace rgc {
     L.coef = o;    o = pair_align16(o + (std::size_t)n_pad * sizeof(float4));
     L.bstart = o;  o = pair_align16(o + (std::size_t)(nbp + 2) * sizeof(int));
     L.pstart = o;  o = pair_align16(o + (std::size_t)(nbp + 2) * sizeof(int));
-    L.tmp = o;     o = pair_align16(o + (std::size_t)(2 * kPWarps) * sizeof(int));
+    L.tmp = o;     o = pair_align16(o + (std::size_t)(2 * (kPairThreads / 32)) * sizeof(int));
     L.slot = o;    o = pair_align16(o + (std::size_t)nslots * sizeof(int2));
     L.chunk = o;   o = pair_align16(o + (std::size_t)nchunks * sizeof(int4));
-    L.wtot = o;    o = pair_align16(o + (std::size_t)kPWarps * kSubPk * sizeof(unsigned));
-    L.run = o;     o = pair_align16(o + (std::size_t)kSub * sizeof(int2));
-    L.cur = o;     o = pair_align16(o + (std::size_t)kSub * kPThreads * sizeof(int));
+    L.wtot = o;    o = pair_align16(o + (std::size_t)2 * 2 * kPairSortWarps * kSubPk * sizeof(unsigned));
+    L.run = o;     o = pair_align16(o + (std::size_t)kPairBufs * kSub * sizeof(int2));
+    L.cur = o;     o = pair_align16(o + (std::size_t)2 * kSub * kPairSortGroup * sizeof(int));
     o = (o + 127) & ~std::size_t(127);
-    L.sorted = o;  o = o + (std::size_t)(kPieceLen + 64 * kSub) * sizeof(float2);
+    L.sorted = o;  o = o + (std::size_t)kPairBufs * kPairBufLen * sizeof(float2);
     L.total  = o;
     return L;
   }
@@ -372,10 +380,12 @@ namespace rgc {
   //   bstart[b] = first sorted entry of bucket b (every bucket padded to an even length)
   //   pstart[b] = first piece of bucket b (pieces of kPieceLen entries, the last one short)
   // entries [0, nb]; tmp: 2 * kPWarps ints.  Ends with a __syncthreads().
+  template <int NT = kPThreads>
   __device__ __forceinline__ void block_scan_buckets(const int* __restrict__ tot, int nb,
                                                      int* bstart, int* pstart, int* tmp) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int kPer = kPMaxBuckets / kPThreads; // 4 consecutive buckets per thread
+    constexpr int kPer   = kPMaxBuckets / NT; // consecutive buckets per thread
+    constexpr int kWarps = NT / 32;
     int pe[kPer], pp[kPer];
     int esum = 0, psum = 0;
 #pragma unroll
@@ -400,14 +410,14 @@ namespace rgc {
     }
     if (lane == 31) {
       tmp[warp]           = ei;
-      tmp[kPWarps + warp] = pi;
+      tmp[kWarps + warp] = pi;
     }
     __syncthreads();
     int ebase = 0, pbase = 0;
 #pragma unroll
-    for (int wq = 0; wq < kPWarps; ++wq) {
+    for (int wq = 0; wq < kWarps; ++wq) {
       ebase += wq < warp ? tmp[wq] : 0;
-      pbase += wq < warp ? tmp[kPWarps + wq] : 0;
+      pbase += wq < warp ? tmp[kWarps + wq] : 0;
     }
     int erun = ebase + ei - esum, prun = pbase + pi - psum;
 #pragma unroll
@@ -783,29 +793,41 @@ namespace rgc {
 
   // ---- kernel 4: the pair loop over the globally bucket-sorted (fc, w).
   //
-  // A piece (<= kPieceLen sorted entries of one bucket) belongs to one warp.  The hinge
-  // r = max(0, fc + fa') of bin j is identically 0 for every particle with fc <= -fa' and
-  // linear in fc for every particle above, so only particles whose fc lies in the same
-  // eighth of the cell as the bin's threshold -fa' need per-pair work; the others enter
-  // through the moments (S0, S1) of their sub-bucket, which the first two lanes of every
-  // sub-bucket's first lane group deliver for free (pair_final_kernel adds that part).
-  // The warp therefore
-  //   1. lands the piece in shared memory with one TMA bulk copy (the next piece's copy is
-  //      issued as soon as the entries sit in registers),
-  //   2. sorts it by sub-bucket s = floor(8 fc) into per-lane cursor order (counting sort,
-  //      every lane owns 16 entries and its own cursor column: no atomics, order fixed by
-  //      (lane, entry)), every run padded to an even length,
-  //   3. streams run s through the lane groups that hold the bins whose threshold lies in
-  //      sub-bucket s (plus, rarely, the neighbouring sub-bucket's groups when a threshold
-  //      sits within the table nodes' wiggle of a boundary): FADD.SAT + FFMA per
-  //      evaluation, fed by broadcast LDS.128,
-  //   4. adds ds_q * sum (fp64) into its private row of the partial sums with RED.ADD.F64
-  //      (one row per warp of the grid: the order of additions is the warp's own).
+  // A piece is <= kPieceLen sorted entries of one bucket.  The hinge r = max(0, fc + fa') of
+  // bin j is identically 0 for every particle with fc <= -fa' and linear in fc for every
+  // particle above, so only particles whose fc lies in the same eighth of the cell as the
+  // bin's threshold -fa' need per-pair work; the others enter through the moments (S0, S1)
+  // of their sub-bucket, which the first two lanes of every sub-bucket's first lane group
+  // deliver for free (pair_final_kernel adds that part).
+  //
+  // One CTA of 16 warps per SM, warp-specialised:
+  //   * warps 8-15 are two SORT groups of four warps.  Group g takes every other piece of the
+  //     CTA into buffer g: 32 coalesced 8-byte loads per thread, counting sort by sub-bucket
+  //     s = floor(8 fc + phi) in (thread, entry) order (6-bit per-thread counters of the 9
+  //     sub-buckets packed into one 64-bit register, warp scans of the counters packed two to a
+  //     register, warp totals through shared memory; no atomics), every run padded to a
+  //     multiple of 64 entries with zero-weight entries.
+  //   * warps 0-7 are the RUN warps: warp w streams run w of the piece (warp 0 also run 8: with
+  //     the phase shift runs 0 and 8 are the two parts of one eighth) through the lane groups
+  //     that hold the bins whose threshold lies in that sub-bucket (plus, rarely, a
+  //     neighbouring sub-bucket's groups, `extmask`), and adds ds_q * sum (fp64) into the CTA's
+  //     row of partial sums with RED.ADD.F64 (a slot is only ever touched by one warp of the
+  //     CTA: the order of additions is fixed).
+  // The hand-over is a pair of named barriers per buffer (FULL: 128 sort threads arrive, 256
+  // run threads wait; EMPTY: the other way round); with four buffers both sort groups work up to
+  // two of their pieces ahead of the run warps.
   // A cell pair next to the table's zero tail (sign < 0) needs sum w max(0, 1 - u): its
   // lanes run the same two instructions on sat(fc + fa0) and the run's S0 lane gives
   // S0 - sum w sat(u), which is exactly 0 when every particle of the run is beyond the
-  // tail (both lanes then execute the identical float sequence).
-  __global__ void __launch_bounds__(kPThreads, 2)
+  // tail (both lanes then execute the identical float sequence and reduction tree).
+  __device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+  }
+  __device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+  }
+
+  __global__ void __launch_bounds__(kPairThreads, 1)
     sync_pair_kernel(const __grid_constant__ PairParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* coef     = reinterpret_cast<float4*>(smem_raw + P.o_coef);
@@ -814,110 +836,109 @@ namespace rgc {
     int*    tmp      = reinterpret_cast<int*>(smem_raw + P.o_tmp);
     int2*   slot_tab = reinterpret_cast<int2*>(smem_raw + P.o_slot);
     int4*   chunks   = reinterpret_cast<int4*>(smem_raw + P.o_chunk);
-    float2* B        = reinterpret_cast<float2*>(smem_raw + P.o_sorted);
-    int*    cur      = reinterpret_cast<int*>(smem_raw + P.o_cur);    // [kSub][kPThreads]
-    unsigned* wtot   = reinterpret_cast<unsigned*>(smem_raw + P.o_wtot); // [kPWarps][kSubPk] packed warp totals -> prefixes
-    int2*   runtab   = reinterpret_cast<int2*>(smem_raw + P.o_run);   // [kSub] {start, padded length}
 
     const int tid  = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int nb   = P.nb;
-    for (int i = tid; i < P.n_pad; i += kPThreads) {
+    for (int i = tid; i < P.n_pad; i += kPairThreads) {
       coef[i] = P.coef_dh[i];
     }
-    for (int i = tid; i < P.nslots; i += kPThreads) {
+    for (int i = tid; i < P.nslots; i += kPairThreads) {
       slot_tab[i] = make_int2(P.slot_i[i].x, __float_as_int(P.slot_f[i].x));
     }
-    for (int i = tid; i < P.nchunks; i += kPThreads) {
+    for (int i = tid; i < P.nchunks; i += kPairThreads) {
       chunks[i] = P.chunks[i];
     }
-    block_scan_buckets(P.tot, nb, bstart, pstart, tmp); // ends with __syncthreads()
+    block_scan_buckets<kPairThreads>(P.tot, nb, bstart, pstart, tmp); // ends with __syncthreads()
 
-    // sub-bucket of a fraction fc in [0, 1]: floor(8 fc + phi) as the round-to-nearest of
-    // 8 fc + (phi - 1/2), taken from the mantissa after adding 1.5 * 2^23 (no F2I on the XU
-    // pipe; phi < 1 keeps the result <= 8; a tie lies within the plan's eps of a boundary, where
-    // either side is valid)
-    const float sub_bias = P.sub_phi - 0.5f;
-    auto sub_of = [&](float fc) {
-      return __float_as_int(fmaf(fc, (float)kSubDiv, sub_bias) + 12582912.0f) & 15;
-    };
     const int npieces = pstart[nb];
-    double*   prow    = P.partials + (std::size_t)blockIdx.x * P.nslots;
-    unsigned long long lane_evals = 0; // hinge evaluations issued by this warp
-    int bcur = 0; // the CTA's pieces ascend: the bucket search resumes where it stopped
-    for (int piece = blockIdx.x; piece < npieces; piece += gridDim.x) {
-      while (pstart[bcur + 1] <= piece) {
-        ++bcur;
-      }
-      const int b   = bcur;
-      const int beg = bstart[b] + (piece - pstart[b]) * kPieceLen;
-      const int n   = min(kPieceLen, bstart[b + 1] - beg); // even
-      // ---- 1. the piece: 16 coalesced 8-byte loads per thread, all in flight at once (entries
-      // beyond a short piece become zero-weight pads); the bucket's chunk table rides along
-      // (used by the runs: those loads complete underneath the sort)
-      float2        ent[kPieceEnt];
-      const float2* src = P.sorted + beg;
+    constexpr int kBarGroup = 1, kBarFull = 3, kBarEmpty = 3 + kPairBufs; // named barriers (+ group / buffer)
+    constexpr int kHandover = kPairSortGroup + kPairRunThreads;
+
+    if (warp >= kPairRunThreads / 32) {
+      // =============================================================== sort groups
+      const int g     = (warp - kPairRunThreads / 32) / (kPairSortGroup / 32);
+      const int pt    = tid - kPairRunThreads - g * kPairSortGroup; // thread of the group
+      const int pwarp = pt >> 5;                                    // warp of the group
+      int*      cur    = reinterpret_cast<int*>(smem_raw + P.o_cur) + g * (kSub * kPairSortGroup);
+      unsigned* wtot   = reinterpret_cast<unsigned*>(smem_raw + P.o_wtot) + g * (2 * kPairSortWarps * kSubPk);
+      // sub-bucket of a fraction fc in [0, 1]: floor(8 fc + phi) as the round-to-nearest of
+      // 8 fc + (phi - 1/2), taken from the mantissa after adding 1.5 * 2^23 (no F2I on the XU
+      // pipe; phi < 1 keeps the result <= 8; a tie lies within the plan's eps of a boundary,
+      // where either side is valid)
+      const float sub_bias = P.sub_phi - 0.5f;
+      auto sub_of = [&](float fc) {
+        return __float_as_int(fmaf(fc, (float)kSubDiv, sub_bias) + 12582912.0f) & 15;
+      };
+      int bcur = 0; // the group's pieces ascend: the bucket search resumes where it stopped
+      for (int k = g;; k += 2) {
+        const long long piece_ll = (long long)blockIdx.x + (long long)k * gridDim.x;
+        if (piece_ll >= npieces) {
+          break;
+        }
+        const int piece = (int)piece_ll;
+        const int buf   = k % kPairBufs; // the group's buffers alternate: it works up to two pieces ahead
+        float2*   B      = reinterpret_cast<float2*>(smem_raw + P.o_sorted) + (std::size_t)buf * kPairBufLen;
+        int2*     runtab = reinterpret_cast<int2*>(smem_raw + P.o_run) + buf * kSub;
+        while (pstart[bcur + 1] <= piece) {
+          ++bcur;
+        }
+        const int beg = bstart[bcur] + (piece - pstart[bcur]) * kPieceLen;
+        const int n   = min(kPieceLen, bstart[bcur + 1] - beg); // even
+        // ---- the piece: 32 coalesced 8-byte loads per thread, all in flight at once (entries
+        // beyond a short piece become zero-weight pads)
+        float2        ent[kPairSortEnt];
+        const float2* src = P.sorted + beg;
 #pragma unroll
-      for (int st = 0; st < kPieceEnt; ++st) {
-        const int e = st * kPThreads + tid;
-        ent[st]     = e < n ? __ldcs(src + e) : make_float2(0.0f, 0.0f);
-      }
-      const unsigned       em     = P.extmask[b];
-      const unsigned char* na_row = P.na_tab + (std::size_t)b * P.nchunks;
-      unsigned             na_reg[3];
+        for (int st = 0; st < kPairSortEnt; ++st) {
+          const int e = st * kPairSortGroup + pt;
+          ent[st]     = e < n ? __ldcs(src + e) : make_float2(0.0f, 0.0f);
+        }
+        unsigned long long cnt = 0ull;
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        na_reg[q] = q * 32 + lane < P.nchunks ? (unsigned)na_row[q * 32 + lane] : 0u;
-      }
-      // ---- 2. counting sort of the piece by sub-bucket, in (thread, entry) order: per-thread
-      // 5-bit counters of the 9 sub-buckets packed into one 64-bit register, warp scans of the
-      // counters packed two to a register, warp totals through shared memory.  Two CTA barriers
-      // per piece: every warp has left the previous piece's runs when the first one opens, and
-      // nothing that the runs read is written before it.
-      unsigned long long cnt = 0ull;
-#pragma unroll
-      for (int st = 0; st < kPieceEnt; ++st) {
-        const int s = sub_of(ent[st].x);
-        cnt += 1ull << (5 * s);
-      }
-      unsigned pk[kSubPk], incl[kSubPk];
-#pragma unroll
-      for (int j = 0; j < kSubPk; ++j) {
-        const unsigned lo = (unsigned)((cnt >> (10 * j)) & 31ull);
-        const unsigned hi = 2 * j + 1 < kSub ? (unsigned)((cnt >> (10 * j + 5)) & 31ull) : 0u;
-        pk[j]   = lo | (hi << 16);
-        incl[j] = pk[j];
-      }
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
+        for (int st = 0; st < kPairSortEnt; ++st) {
+          cnt += 1ull << (6 * sub_of(ent[st].x));
+        }
+        unsigned pk[kSubPk], incl[kSubPk];
 #pragma unroll
         for (int j = 0; j < kSubPk; ++j) {
-          const unsigned t = __shfl_up_sync(0xffffffffu, incl[j], off);
-          if (lane >= off) {
-            incl[j] += t;
+          const unsigned lo = (unsigned)((cnt >> (12 * j)) & 63ull);
+          const unsigned hi = 2 * j + 1 < kSub ? (unsigned)((cnt >> (12 * j + 6)) & 63ull) : 0u;
+          pk[j]   = lo | (hi << 16);
+          incl[j] = pk[j];
+        }
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+          for (int j = 0; j < kSubPk; ++j) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl[j], off);
+            if (lane >= off) {
+              incl[j] += t;
+            }
           }
         }
-      }
-      if (lane == 31) {
+        // warp totals, double-buffered by the group's piece parity (a fast warp may write the
+        // next piece's totals while a slow one still reads this piece's)
+        unsigned* wt = wtot + ((k >> 1) & 1) * (kPairSortWarps * kSubPk);
+        if (lane == 31) {
 #pragma unroll
-        for (int j = 0; j < kSubPk; ++j) {
-          wtot[warp * kSubPk + j] = incl[j];
+          for (int j = 0; j < kSubPk; ++j) {
+            wt[pwarp * kSubPk + j] = incl[j];
+          }
         }
-      }
-      __syncthreads();
-      // every warp for itself: (packed) prefix over the warps before it, totals, padded run starts
-      unsigned pre_pk = 0u, tot_pk = 0u;
-      if (lane < kSubPk) {
+        named_bar_sync(kBarGroup + g, kPairSortGroup);
+        // every warp for itself: (packed) prefix over the group's warps before it, totals,
+        // padded run starts
+        unsigned pre_pk = 0u, tot_pk = 0u;
+        if (lane < kSubPk) {
 #pragma unroll
-        for (int w = 0; w < kPWarps; ++w) {
-          const unsigned t = wtot[w * kSubPk + lane];
-          pre_pk += w < warp ? t : 0u;
-          tot_pk += t;
+          for (int w = 0; w < kPairSortWarps; ++w) {
+            const unsigned t = wt[w * kSubPk + lane];
+            pre_pk += w < pwarp ? t : 0u;
+            tot_pk += t;
+          }
         }
-      }
-      int start_k; // lane k: first sorted entry of run k
-      {
         const unsigned tp  = __shfl_sync(0xffffffffu, tot_pk, lane >> 1);
         const int      tot = lane < kSub ? (int)((tp >> ((lane & 1) * 16)) & 0xffffu) : 0;
         const int      pad = (tot + 63) & ~63; // two particles per lane and loop iteration
@@ -929,33 +950,64 @@ namespace rgc {
             inc += t;
           }
         }
-        start_k = inc - pad;
-        if (warp == 0 && lane < kSub) {
+        const int start_k = inc - pad; // lane k: first sorted entry of run k
+        // the buffer is free again once the run warps have left the piece that used it before
+        if (k >= kPairBufs) {
+          named_bar_sync(kBarEmpty + buf, kHandover);
+        }
+        if (pwarp == 0 && lane < kSub) {
           runtab[lane] = make_int2(start_k, pad);
           for (int i = tot; i < pad; ++i) {
             B[start_k + i] = make_float2(0.0f, 0.0f); // zero-weight pad
           }
         }
-      }
 #pragma unroll
-      for (int k = 0; k < kSub; ++k) {
-        const unsigned sh   = (k & 1) * 16;
-        const int      st_k = __shfl_sync(0xffffffffu, start_k, k);
-        const unsigned pr   = __shfl_sync(0xffffffffu, pre_pk, k >> 1);
-        cur[k * kPThreads + tid] =
-          st_k + (int)((pr >> sh) & 0xffffu) + (int)(((incl[k >> 1] - pk[k >> 1]) >> sh) & 0xffffu);
-      }
-      {
-        unsigned long long seen = 0ull;
-#pragma unroll
-        for (int st = 0; st < kPieceEnt; ++st) {
-          const int s    = sub_of(ent[st].x);
-          const int rank = (int)((seen >> (5 * s)) & 31ull);
-          seen += 1ull << (5 * s);
-          B[cur[s * kPThreads + tid] + rank] = ent[st];
+        for (int kk = 0; kk < kSub; ++kk) {
+          const unsigned sh   = (kk & 1) * 16;
+          const int      st_k = __shfl_sync(0xffffffffu, start_k, kk);
+          const unsigned pr   = __shfl_sync(0xffffffffu, pre_pk, kk >> 1);
+          cur[kk * kPairSortGroup + pt] =
+            st_k + (int)((pr >> sh) & 0xffffu) + (int)(((incl[kk >> 1] - pk[kk >> 1]) >> sh) & 0xffffu);
         }
+        // the thread's cursor column is its own: read, bump, store
+#pragma unroll
+        for (int st = 0; st < kPairSortEnt; ++st) {
+          int* c        = cur + sub_of(ent[st].x) * kPairSortGroup + pt;
+          const int pos = *c;
+          *c            = pos + 1;
+          B[pos]        = ent[st];
+        }
+        named_bar_arrive(kBarFull + buf, kHandover);
       }
-      __syncthreads();
+      return;
+    }
+
+    // ================================================================= run warps
+    double*   prow    = P.partials + (std::size_t)blockIdx.x * P.nslots;
+    unsigned long long lane_evals = 0; // hinge evaluations issued by this warp
+    int bcur = 0;
+    for (int k = 0;; ++k) {
+      const long long piece_ll = (long long)blockIdx.x + (long long)k * gridDim.x;
+      if (piece_ll >= npieces) {
+        break;
+      }
+      const int piece = (int)piece_ll;
+      const int buf   = k % kPairBufs;
+      while (pstart[bcur + 1] <= piece) {
+        ++bcur;
+      }
+      const int b = bcur;
+      const float2* B      = reinterpret_cast<const float2*>(smem_raw + P.o_sorted) + (std::size_t)buf * kPairBufLen;
+      const int2*   runtab = reinterpret_cast<const int2*>(smem_raw + P.o_run) + buf * kSub;
+      // the bucket's chunk table (these loads complete while the warp waits for the piece)
+      const unsigned       em     = P.extmask[b];
+      const unsigned char* na_row = P.na_tab + (std::size_t)b * P.nchunks;
+      unsigned             na_reg[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        na_reg[q] = q * 32 + lane < P.nchunks ? (unsigned)na_row[q * 32 + lane] : 0u;
+      }
+      named_bar_sync(kBarFull + buf, kHandover);
       // ---- 3. the runs
       float* pm    = P.piece_mom + (std::size_t)piece * kMomStride;
       float  s0run = 0.0f;
@@ -1050,7 +1102,7 @@ namespace rgc {
       // warp w streams run w (warp 0 also run 8: with the phase shift runs 0 and 8 are the two
       // parts of one eighth)
 #pragma unroll 1
-      for (int r = warp; r < kSub; r += kPWarps) {
+      for (int r = warp; r < kSub; r += kPairRunThreads / 32) {
         const int2 rt = runtab[r];
         if (rt.y == 0) {
           if (lane < 2) {
@@ -1066,6 +1118,10 @@ namespace rgc {
         if (r > 0 && ((em >> (kSub + r - 1)) & 1u)) {
           do_chunks(r - 1, false, r, re, rt.y); // a threshold of sub-bucket r - 1 strays up here
         }
+      }
+      // hand the buffer back if the sort group will use it again
+      if (piece_ll + (long long)kPairBufs * gridDim.x < npieces) {
+        named_bar_arrive(kBarEmpty + buf, kHandover);
       }
     }
     if (lane == 0 && lane_evals != 0ull) {
@@ -1351,6 +1407,9 @@ namespace rgc {
       double phi = 1.0 - centre;
       phi -= std::floor(phi);
       pp.sub_phi = (float)phi;
+      if (const char* fp = std::getenv("RGC_PAIR_PHI")) { // test knob: force the phase (e.g. 0 puts
+        pp.sub_phi = (float)std::atof(fp);                // BASELINE's thresholds ON the boundaries)
+      }
       if (!(pp.sub_phi >= 0.0f && pp.sub_phi < 1.0f)) {
         pp.sub_phi = 0.0f;
       }
@@ -1456,6 +1515,7 @@ namespace rgc {
     std::vector<float>  key_bins;  // e_syn of the chunk's bins, in slot order
     std::vector<int>    key_index; // their indices in the caller's bin array
     std::vector<double> key_tx, key_y;
+    std::string         key_phi; // RGC_PAIR_PHI (test knob) the plan was made under
     PairPlan            pp;
     char*               dev { nullptr };
     std::size_t         off_map { 0 }, off_si { 0 }, off_sf { 0 }, off_dh { 0 }, off_vs { 0 };
@@ -1504,8 +1564,10 @@ namespace rgc {
     for (std::size_t s = 0; s < bins.size(); ++s) {
       kb[s] = bins_e_syn[bins[s]];
     }
+    const char*       fp = std::getenv("RGC_PAIR_PHI");
+    const std::string key_phi = fp ? fp : "";
     for (const auto& e : cache) {
-      if (e.key_index == bins && e.key_bins.size() == kb.size() &&
+      if (e.key_phi == key_phi && e.key_index == bins && e.key_bins.size() == kb.size() &&
           std::memcmp(e.key_bins.data(), kb.data(), kb.size() * sizeof(float)) == 0 &&
           e.key_tx == tp.tx && e.key_y == tp.y) {
         *out = &e;
@@ -1520,6 +1582,7 @@ namespace rgc {
     CachedPlan e;
     e.key_bins  = kb;
     e.key_index = bins;
+    e.key_phi   = key_phi;
     e.key_tx    = tp.tx;
     e.key_y     = tp.y;
     make_pair_plan(tp, bins_e_syn, bins, e.pp);
@@ -1659,7 +1722,7 @@ namespace rgc {
     const Geom        g0    = geom_for(cnt0);
     const int         rows0 = g0.rows;
     const std::size_t npad0 = (std::size_t)g0.ntiles * kPTile;
-    const int  pair_ctas = c.sm_count * 2;
+    const int  pair_ctas = c.sm_count; // one warp-specialised CTA of 16 warps per SM
     const std::size_t max_pieces  = cnt0 / kPieceLen + (std::size_t)pp.nbp + 2;
     auto align = [](std::size_t x) { return (x + 255) & ~std::size_t(255); };
     const std::size_t off_msum = 0;
@@ -1762,7 +1825,7 @@ namespace rgc {
       RGC_CUDA(cudaGetLastError());
       RGC_CUDA(cudaEventRecord(c.ev[5], c.stream));
       RGC_CUDA(cudaMemsetAsync(P.partials, 0, part_bytes, c.stream));
-      sync_pair_kernel<<<pair_ctas, kPThreads, smem, c.stream>>>(P);
+      sync_pair_kernel<<<pair_ctas, kPairThreads, smem, c.stream>>>(P);
       RGC_CUDA(cudaGetLastError());
       RGC_CUDA(cudaEventRecord(c.ev[4], c.stream));
       pair_moments_kernel<<<pp.nb, kPThreads, 0, c.stream>>>(

@@ -336,6 +336,44 @@ def test_zero_group_skipping_is_exact(cabi, monkeypatch, nbins, lo, hi, hinge):
     assert 0.9 * 400_000 * 32 <= issued_all < 0.5 * 400_000 * nbins
 
 
+@pytest.mark.parametrize("phi", ["0", "0.5", "0.999"])
+def test_sub_bucket_boundaries_on_thresholds(cabi, port, monkeypatch, hinge, phi):
+    """BASELINE's 200 bins over 7 decades on the 200-point table over 8 decades put every hinge
+    threshold on a multiple of 1/8 of a cell.  The plan moves the sub-bucket boundaries away from
+    them (phase 0.5 there); forcing the phase to 0 puts every threshold ON a boundary, where the
+    table nodes' 1e-5 wiggle decides per bucket which neighbouring run a lane group must also
+    see (extmask): same spectrum, same exact zeros, more evaluations"""
+    U, E, B = synth.config3(300_000, seed=11)
+    bins = cabi.logspace(0.01, 1e5, 200)
+    p = _particles(cabi, U, E, B)
+    base = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)[1]
+    issued0 = cabi.last_pair_lane_evals()
+    monkeypatch.setenv("RGC_PAIR_PHI", phi)
+    got = cabi.sync_spectrum_particles(p, bins, 1.0, 1.0, 1.0)[1]  # (the plan cache is keyed by the knob too)
+    issued = cabi.last_pair_lane_evals()
+    monkeypatch.delenv("RGC_PAIR_PHI")
+    _, want = port.sync_spectrum_particles(U, E, B, bins, 1.0, 1.0, 1.0)
+    assert synth.rel_err(got, want) < 1e-5
+    assert np.all(got[want == 0] == 0)
+    assert synth.rel_err(got, base) < 2e-6
+    if phi == "0":
+        assert issued > 1.5 * issued0  # lane groups also stream the neighbouring runs
+
+
+@pytest.mark.parametrize("nbins,lo,hi", [(1, 1.0, 2.0), (2, 0.1, 10.0), (31, 1e-2, 1e4), (33, 1e-2, 1e4),
+                                         (257, 1e-3, 1e6), (2032, 1e-3, 1e6), (2500, 1e-3, 1e6)])
+def test_hinge_bin_counts(cabi, port, hinge, nbins, lo, hi):
+    """lane-group bookkeeping of the sub-bucket plan: a single bin, bins that do not fill a lane
+    group, several groups per sub-bucket, the per-launch maximum and beyond it (two launches)"""
+    U, E, B = synth.full3d(40_000, seed=5)
+    bins = cabi.logspace(lo, hi, nbins) if nbins > 1 else np.array([1.5], np.float32)
+    p = _particles(cabi, U, E, B)
+    got = cabi.sync_spectrum_particles(p, bins, 1.3, 2.0, 0.7)[1]
+    _, want = port.sync_spectrum_particles(U, E, B, bins, 1.3, 2.0, 0.7)
+    assert synth.rel_err(got, want, floor_frac=1e-3) < 1e-4  # 4e4 particles do not average the rounding
+    assert np.all(got[want == 0] == 0)
+
+
 def test_config3_at_1e7(cabi, port):
     """SURVEY.md 8d configs 2-3 at 1e7 particles (the oracle needs ~10 s on the box's host
     threads): spectrum <= 1e-5 per bin against the reference's float terms summed in double,
