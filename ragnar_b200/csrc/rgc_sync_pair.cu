@@ -1634,7 +1634,10 @@ namespace rgc {
     if (cached_pair_plan(tp, bins_e_syn, bins, &cp) != RGC_OK) {
       return false;
     }
-    return cp->pp.ok && cp->pp.ngroups <= kPMaxGroups;
+    const PairPlan& pp = cp->pp;
+    // (a very wide table with ~2000 bins can outgrow the pair kernel's shared memory)
+    const bool fits = pair_smem_layout(pp.n_pad, pp.nbp, pp.nslots, (int)pp.chunks.size()).total <= 226 * 1024;
+    return pp.ok && pp.ngroups <= kPMaxGroups && pp.nb < kPMaxBuckets && pp.nbp <= kPMaxBuckets && fits;
   }
 
   // Runs rank_order_probe_kernel once per process (per device context) and remembers the verdict.
