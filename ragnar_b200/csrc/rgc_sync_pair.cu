@@ -852,7 +852,16 @@ namespace rgc {
     }
     block_scan_buckets<kPairThreads>(P.tot, nb, bstart, pstart, tmp); // ends with __syncthreads()
 
-    const int npieces = pstart[nb];
+    // pieces are dealt to the CTAs in consecutive pairs (two consecutive pieces mostly share their
+    // bucket; buckets differ in cost, so the pairs of a CTA are spread over all of them): the
+    // CTA's k-th piece is piece_of(k)
+    const int npieces   = pstart[nb];
+    const int npairs    = (npieces + 1) / 2;
+    const int my_pairs  = (int)blockIdx.x < npairs ? (npairs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int last_pair = (int)blockIdx.x + (my_pairs - 1) * (int)gridDim.x;
+    // (the globally last pair may hold a single piece)
+    const int my_pieces = my_pairs == 0 ? 0 : 2 * my_pairs - ((2 * last_pair + 1 >= npieces) ? 1 : 0);
+    auto piece_of = [&](int k) { return 2 * ((int)blockIdx.x + (k >> 1) * (int)gridDim.x) + (k & 1); };
     constexpr int kBarGroup = 1, kBarFull = 3, kBarEmpty = 3 + kPairBufs; // named barriers (+ group / buffer)
     constexpr int kHandover = kPairSortGroup + kPairRunThreads;
 
@@ -869,15 +878,11 @@ namespace rgc {
       // where either side is valid)
       const float sub_bias = P.sub_phi - 0.5f;
       auto sub_of = [&](float fc) {
-        return __float_as_int(fmaf(fc, (float)kSubDiv, sub_bias) + 12582912.0f) & 15;
+        return min(__float_as_int(fmaf(fc, (float)kSubDiv, sub_bias) + 12582912.0f) & 15, kSub - 1);
       };
       int bcur = 0; // the group's pieces ascend: the bucket search resumes where it stopped
-      for (int k = g;; k += 2) {
-        const long long piece_ll = (long long)blockIdx.x + (long long)k * gridDim.x;
-        if (piece_ll >= npieces) {
-          break;
-        }
-        const int piece = (int)piece_ll;
+      for (int k = g; k < my_pieces; k += 2) {
+        const int piece = piece_of(k);
         const int buf   = k % kPairBufs; // the group's buffers alternate: it works up to two pieces ahead
         float2*   B      = reinterpret_cast<float2*>(smem_raw + P.o_sorted) + (std::size_t)buf * kPairBufLen;
         int2*     runtab = reinterpret_cast<int2*>(smem_raw + P.o_run) + buf * kSub;
@@ -886,14 +891,16 @@ namespace rgc {
         }
         const int beg = bstart[bcur] + (piece - pstart[bcur]) * kPieceLen;
         const int n   = min(kPieceLen, bstart[bcur + 1] - beg); // even
-        // ---- the piece: 32 coalesced 8-byte loads per thread, all in flight at once (entries
-        // beyond a short piece become zero-weight pads)
+        // ---- the piece: 16 coalesced 16-byte loads (two entries) per thread, all in flight at
+        // once (entries beyond a short piece become zero-weight pads; beg and n are even)
         float2        ent[kPairSortEnt];
-        const float2* src = P.sorted + beg;
+        const float4* src = reinterpret_cast<const float4*>(P.sorted + beg);
 #pragma unroll
-        for (int st = 0; st < kPairSortEnt; ++st) {
-          const int e = st * kPairSortGroup + pt;
-          ent[st]     = e < n ? __ldcs(src + e) : make_float2(0.0f, 0.0f);
+        for (int st = 0; st < kPairSortEnt / 2; ++st) {
+          const int    e2 = st * kPairSortGroup + pt;
+          const float4 v  = 2 * e2 < n ? __ldcs(src + e2) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          ent[2 * st]     = make_float2(v.x, v.y);
+          ent[2 * st + 1] = make_float2(v.z, v.w);
         }
         unsigned long long cnt = 0ull;
 #pragma unroll
@@ -983,22 +990,25 @@ namespace rgc {
     }
 
     // ================================================================= run warps
+    // Two consecutive pieces of the same bucket are streamed as one: the set-up of a lane group
+    // (32 broadcasts of fa') and its transpose-reduction are paid once for both.
     double*   prow    = P.partials + (std::size_t)blockIdx.x * P.nslots;
     unsigned long long lane_evals = 0; // hinge evaluations issued by this warp
     int bcur = 0;
-    for (int k = 0;; ++k) {
-      const long long piece_ll = (long long)blockIdx.x + (long long)k * gridDim.x;
-      if (piece_ll >= npieces) {
-        break;
-      }
-      const int piece = (int)piece_ll;
+    for (int k = 0; k < my_pieces;) {
+      const int piece = piece_of(k);
       const int buf   = k % kPairBufs;
       while (pstart[bcur + 1] <= piece) {
         ++bcur;
       }
-      const int b = bcur;
-      const float2* B      = reinterpret_cast<const float2*>(smem_raw + P.o_sorted) + (std::size_t)buf * kPairBufLen;
-      const int2*   runtab = reinterpret_cast<const int2*>(smem_raw + P.o_run) + buf * kSub;
+      const int  b      = bcur;
+      // the second piece of the pair, if it belongs to the same bucket
+      const bool paired = (k & 1) == 0 && k + 1 < my_pieces && pstart[b + 1] > piece + 1;
+      const int  buf2   = (k + 1) % kPairBufs;
+      const float2* BA   = reinterpret_cast<const float2*>(smem_raw + P.o_sorted) + (std::size_t)buf * kPairBufLen;
+      const float2* BB   = reinterpret_cast<const float2*>(smem_raw + P.o_sorted) + (std::size_t)buf2 * kPairBufLen;
+      const int2*   runA = reinterpret_cast<const int2*>(smem_raw + P.o_run) + buf * kSub;
+      const int2*   runB = reinterpret_cast<const int2*>(smem_raw + P.o_run) + buf2 * kSub;
       // the bucket's chunk table (these loads complete while the warp waits for the piece)
       const unsigned       em     = P.extmask[b];
       const unsigned char* na_row = P.na_tab + (std::size_t)b * P.nchunks;
@@ -1008,20 +1018,25 @@ namespace rgc {
         na_reg[q] = q * 32 + lane < P.nchunks ? (unsigned)na_row[q * 32 + lane] : 0u;
       }
       named_bar_sync(kBarFull + buf, kHandover);
-      // ---- 3. the runs
-      float* pm    = P.piece_mom + (std::size_t)piece * kMomStride;
-      float  s0run = 0.0f;
-      // One lane group (32 bins, lane = bin in the slot tables) over the run [re, re + len), with
-      // the roles swapped for the loop: a lane owns every 32nd PARTICLE of the run and keeps the
-      // partial sums of all 32 bins in registers (the 32 fa' are warp-uniform register copies), so
-      // the loop is r = sat(fc + fa'_j), acc_j += w r for j = 0..31 per particle with no shared
-      // memory traffic beyond one coalesced 8-byte load per particle (a broadcast load per
-      // particle made the lanes = bins form shared-memory bound at one lane group: 1 wavefront
-      // per 2 instructions).  A butterfly transpose-reduction then leaves bin j's total in lane j.
-      // The same instruction sequence and the same reduction tree serve every bin, so the zero-tail
-      // bins (S0 - sum w sat(u)) are exactly 0 when every particle of the run is beyond the tail.
+      if (paired) {
+        named_bar_sync(kBarFull + buf2, kHandover);
+      }
+      // ---- the runs.  The moments of a pair of pieces go to the second piece's slot.
+      float* pm_zero = P.piece_mom + (std::size_t)piece * kMomStride;
+      float* pm      = paired ? pm_zero + kMomStride : pm_zero;
+      float  s0run   = 0.0f;
+      // One lane group (32 bins, lane = bin in the slot tables) over the run(s), with the roles
+      // swapped for the loop: a lane owns every 32nd PARTICLE of a run and keeps the partial sums
+      // of all 32 bins in registers (the 32 fa' are warp-uniform register copies), so the loop is
+      // r = sat(fc + fa'_j), acc_j += w r for j = 0..31 per particle with no shared-memory traffic
+      // beyond one coalesced 8-byte load per particle (a broadcast load per particle made the
+      // lanes = bins form shared-memory bound at one lane group: 1 wavefront per 2 instructions).
+      // A butterfly transpose-reduction then leaves bin j's total in lane j.  The same instruction
+      // sequence and the same reduction tree serve every bin, so the zero-tail bins
+      // (S0 - sum w sat(u)) are exactly 0 when every particle of the run is beyond the tail.
       auto run_group = [&](const int group, const bool moments, const int r,
-                           const float2* __restrict__ re, const int len) {
+                           const float2* __restrict__ reA, const int lenA,
+                           const float2* __restrict__ reB, const int lenB) {
         const int2   sl    = slot_tab[group * 32 + lane];
         const float  fa0   = __int_as_float(sl.y);
         const float4 dh    = coef[max(sl.x + b, 0)];
@@ -1037,10 +1052,22 @@ namespace rgc {
         }
         // runs are padded to a multiple of 64 entries: two particles per lane and iteration, the
         // next two in flight
-        float2 p0 = re[lane], p1 = re[32 + lane];
+        auto stream = [&](const float2* __restrict__ re, const int len) {
+          float2 p0 = re[lane], p1 = re[32 + lane];
 #pragma unroll 1
-        for (int e = 64; e < len; e += 64) {
-          const float2 n0 = re[e + lane], n1 = re[e + 32 + lane];
+          for (int e = 64; e < len; e += 64) {
+            const float2 n0 = re[e + lane], n1 = re[e + 32 + lane];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              acc[j] = fmaf(p0.y, __saturatef(p0.x + f[j]), acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              acc[j] = fmaf(p1.y, __saturatef(p1.x + f[j]), acc[j]);
+            }
+            p0 = n0;
+            p1 = n1;
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             acc[j] = fmaf(p0.y, __saturatef(p0.x + f[j]), acc[j]);
@@ -1049,16 +1076,12 @@ namespace rgc {
           for (int j = 0; j < 32; ++j) {
             acc[j] = fmaf(p1.y, __saturatef(p1.x + f[j]), acc[j]);
           }
-          p0 = n0;
-          p1 = n1;
+        };
+        if (lenA > 0) {
+          stream(reA, lenA);
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          acc[j] = fmaf(p0.y, __saturatef(p0.x + f[j]), acc[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          acc[j] = fmaf(p1.y, __saturatef(p1.x + f[j]), acc[j]);
+        if (lenB > 0) {
+          stream(reB, lenB);
         }
         // transpose-reduce: after the stage with partner lane ^ off a lane keeps the half of its
         // values whose bin index has that bit equal to its own; lane j ends with bin j
@@ -1076,7 +1099,7 @@ namespace rgc {
         if (moments) {
           s0run = __shfl_sync(0xffffffffu, s2, 0);
           if (lane < 2) {
-            pm[r * 2 + lane] = s2; // lanes 0 / 1 of the sub-bucket's first group: S0 / S1 of the run
+            pm[r * 2 + lane] = s2; // lanes 0 / 1 of the sub-bucket's first group: S0 / S1 of the run(s)
           }
         }
         if (ds != 0.0f) {
@@ -1087,15 +1110,16 @@ namespace rgc {
                        : "memory");
         }
       };
-      auto do_chunks = [&](const int sub, const bool own, const int r, const float2* re, const int len) {
+      auto do_chunks = [&](const int sub, const bool own, const int r, const float2* reA, const int lenA,
+                           const float2* reB, const int lenB) {
         for (int c = P.chunk_first[sub]; c < P.chunk_first[sub + 1]; ++c) {
           const int4     ch  = chunks[c];
           const unsigned nav = c < 32 ? na_reg[0] : (c < 64 ? na_reg[1] : na_reg[2]);
           const int      na  = P.force_groups != 0u ? ch.y : (int)__shfl_sync(0xffffffffu, nav, c & 31);
           // the first na lane groups of the chunk are on the table for this bucket
-          lane_evals += (unsigned long long)len * (unsigned)(na * 32);
+          lane_evals += (unsigned long long)(lenA + lenB) * (unsigned)(na * 32);
           for (int g = 0; g < na; ++g) {
-            run_group(ch.x + g, own && ch.z != 0 && g == 0, r, re, len);
+            run_group(ch.x + g, own && ch.z != 0 && g == 0, r, reA, lenA, reB, lenB);
           }
         }
       };
@@ -1103,26 +1127,35 @@ namespace rgc {
       // parts of one eighth)
 #pragma unroll 1
       for (int r = warp; r < kSub; r += kPairRunThreads / 32) {
-        const int2 rt = runtab[r];
-        if (rt.y == 0) {
+        const int2 rtA = runA[r];
+        const int2 rtB = paired ? runB[r] : make_int2(0, 0);
+        if (paired && lane < 2) {
+          pm_zero[r * 2 + lane] = 0.0f; // the pair's moments are booked under the second piece
+        }
+        if (rtA.y + rtB.y == 0) {
           if (lane < 2) {
             pm[r * 2 + lane] = 0.0f;
           }
           continue;
         }
-        const float2* re = B + rt.x;
-        do_chunks(r, true, r, re, rt.y); // the sub-bucket's own bins (first group: moment lanes)
+        const float2* reA = BA + rtA.x;
+        const float2* reB = BB + rtB.x;
+        do_chunks(r, true, r, reA, rtA.y, reB, rtB.y); // the sub-bucket's own bins (first group: moment lanes)
         if (r + 1 < kSub && ((em >> (r + 1)) & 1u)) {
-          do_chunks(r + 1, false, r, re, rt.y); // a threshold of sub-bucket r + 1 strays down here
+          do_chunks(r + 1, false, r, reA, rtA.y, reB, rtB.y); // a threshold of sub-bucket r + 1 strays down here
         }
         if (r > 0 && ((em >> (kSub + r - 1)) & 1u)) {
-          do_chunks(r - 1, false, r, re, rt.y); // a threshold of sub-bucket r - 1 strays up here
+          do_chunks(r - 1, false, r, reA, rtA.y, reB, rtB.y); // a threshold of sub-bucket r - 1 strays up here
         }
       }
-      // hand the buffer back if the sort group will use it again
-      if (piece_ll + (long long)kPairBufs * gridDim.x < npieces) {
+      // hand the buffers back if a sort group will use them again
+      if (k + kPairBufs < my_pieces) {
         named_bar_arrive(kBarEmpty + buf, kHandover);
       }
+      if (paired && k + 1 + kPairBufs < my_pieces) {
+        named_bar_arrive(kBarEmpty + buf2, kHandover);
+      }
+      k += paired ? 2 : 1;
     }
     if (lane == 0 && lane_evals != 0ull) {
       atomicAdd(P.lane_evals, lane_evals);
