@@ -5,8 +5,9 @@
 Every rank owns shard_range(n, rank, world) of one seeded host population; the NCCL
 all-reduced spectrum / histogram of the sharded run must match the CPU oracle on the
 whole population (spectrum <= 1e-5 per bin, counts bit-exact and identical for every
-world size) and a one-rank run of the same library (<= 1e-6: the hinge sums are float
-per piece of <= 1024 sorted particles, and the pieces depend on the partition)."""
+world size) and a one-rank run of the same library (<= 1e-5: the hinge sums are float
+per run of a <= 4096-entry piece, the pieces depend on the partition, and shards of up to
+2^19 particles take the literal path)."""
 import os
 import sys
 from pathlib import Path
