@@ -286,14 +286,27 @@ int rgc_last_kernel_ms(float ms[2]);
 int rgc_last_kernel_times(float* ms, int n);
 
 /* Hinge evaluations (32 per lane group and sorted entry) the pair kernel actually issued
- * in the last rgc_sync_spectrum_particles call on this rank: lane groups whose bins are
- * all beyond the table's zero tail for a bucket are skipped, so this is <= the
- * particles x bins of the call rounded up to whole groups (roofline accounting). */
+ * in the last rgc_sync_spectrum_particles call on this rank.  A particle is streamed only
+ * through the lane groups of the bins whose hinge threshold lies in the particle's own
+ * sub-bucket of the table cell (about one pair in eight; the rest enters through sub-bucket
+ * moments), and lane groups whose bins are all beyond the table's zero tail for a bucket are
+ * skipped (roofline accounting). */
 int rgc_last_pair_lane_evals(double* lane_evals);
 /* (particle, bin) pairs of the last rgc_sync_spectrum_particles call on this rank whose table
  * cell pair is not identically zero — what an ideal kernel would have to evaluate (the
  * whole-step roofline of bench.py); counted on the device by pair_moments_kernel. */
 int rgc_last_pair_ontable_evals(double* evals);
+/* Host-only description of the hinge path's plan for photon bins (e_syn, any order) on an F
+ * table — no device needed; what the CPU tests check.  info[0] 1 if the hinge path takes these
+ * bins, [1] lane groups, [2] slots (32 per group), [3] buckets, [4] chunks of <= 8 groups,
+ * [5] buckets in which some sub-bucket's groups also see a neighbouring run, [6] most groups of
+ * one sub-bucket, [7] sub-buckets per table cell; *phase = the phase phi of the sub-bucket
+ * boundaries, s = floor(8 fc + phi); slot_bin[i] = index of the bin that slot i carries, -1 for
+ * moment lanes and spare lanes (at most cap entries are written).  Replaces nothing in the
+ * reference (its MDRange visits every pair, src/physics/synchrotron.cpp:124-139). */
+int rgc_pair_plan_describe(const float* bins_e_syn, size_t nbins, const float* tab_x,
+                           const float* tab_y, size_t tab_n, int info[8], float* phase,
+                           int* slot_bin, size_t cap);
 /* How the bucket sort of the hinge pipeline ranks particles: 1 = one shared-memory atomic per
  * particle, after a probe kernel verified ON THIS DEVICE that the lanes of one instruction
  * hitting one address are served in lane order (what makes results bitwise reproducible);

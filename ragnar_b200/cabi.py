@@ -89,6 +89,9 @@ SIGNATURES = {
     "rgc_last_pair_lane_evals": (C.c_int, [_f64p]),
     "rgc_last_pair_ontable_evals": (C.c_int, [_f64p]),
     "rgc_sort_rank_mode": (C.c_int, [C.POINTER(C.c_int)]),
+    "rgc_pair_plan_describe": (C.c_int, [_f32p, C.c_size_t, _f32p, _f32p, C.c_size_t,
+                                         C.POINTER(C.c_int), C.POINTER(C.c_float),
+                                         C.POINTER(C.c_int), C.c_size_t]),
     "rgc_comm_exchange_kind": (C.c_int, [C.POINTER(C.c_int)]),
     "rgc_measure_peak": (C.c_int, [C.c_int, _f64p, _f64p]),
     "rgc_h5_open": (C.c_int, [C.c_char_p, C.c_int, _vpp]),
@@ -208,6 +211,25 @@ def sort_rank_mode() -> int:
     m = C.c_int()
     check(lib().rgc_sort_rank_mode(C.byref(m)))
     return m.value
+
+
+def pair_plan_describe(bins, tab_x, tab_y) -> dict:
+    """host-only: how the hinge path lays the photon bins out in lane groups (no device needed)"""
+    bins = np.ascontiguousarray(bins, np.float32)
+    tx = np.ascontiguousarray(tab_x, np.float32)
+    ty = np.ascontiguousarray(tab_y, np.float32)
+    info = (C.c_int * 8)()
+    phase = C.c_float()
+    cap = 32 * 128
+    slot_bin = (C.c_int * cap)()
+    check(lib().rgc_pair_plan_describe(bins.ctypes.data_as(_f32p), bins.size, tx.ctypes.data_as(_f32p),
+                                       ty.ctypes.data_as(_f32p), tx.size, info, C.byref(phase), slot_bin, cap))
+    keys = ("eligible", "groups", "slots", "buckets", "chunks", "buckets_with_extension",
+            "most_groups_per_sub_bucket", "sub_buckets")
+    out = dict(zip(keys, list(info)))
+    out["phase"] = float(phase.value)
+    out["slot_bin"] = np.array(slot_bin[:out["slots"]], np.int32)
+    return out
 
 
 def trim_memory() -> None:

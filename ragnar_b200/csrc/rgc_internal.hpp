@@ -165,6 +165,8 @@ namespace rgc {
                          float* main_ms, bool defer_sync);
   // after the caller's own stream synchronisation: kernel times of a deferred pass
   int  collect_pair_times(float* main_ms);
+  void pair_plan_describe(const TablePlan& tp, const float* bins_e_syn, const std::vector<int>& bins,
+                          int info[8], float* phase, int* slot_bin, std::size_t cap);
   bool pair_single_pass(std::size_t n); // n particles fit one pipeline pass
   void pair_release_plans();            // frees the cached device plans (rgc_finalize)
   int  pair_rank_mode(); // verdict of the rank-order probe: -1 not run, 0 ballots, 1 atomics

@@ -1542,6 +1542,47 @@ namespace rgc {
     }
   }
 
+  // Host-only summary of the plan (rgc_pair_plan_describe; CPU tests of the lane-group layout)
+  void pair_plan_describe(const TablePlan& tp, const float* bins_e_syn, const std::vector<int>& bins,
+                          int info[8], float* phase, int* slot_bin, std::size_t cap) {
+    info[0] = 0;
+    for (int k = 1; k < 8; ++k) {
+      info[k] = 0;
+    }
+    if (!pair_shape_eligible(tp, bins_e_syn, bins)) {
+      return;
+    }
+    PairPlan pp;
+    make_pair_plan(tp, bins_e_syn, bins, pp);
+    int ext = 0, most = 0;
+    for (unsigned m : pp.extmask) {
+      ext += m != 0u ? 1 : 0;
+    }
+    for (int s = 0; s < kSub; ++s) {
+      int groups = 0;
+      for (int c = pp.chunk_first[s]; c < pp.chunk_first[s + 1]; ++c) {
+        groups += pp.chunks[c].y;
+      }
+      most = std::max(most, groups);
+    }
+    const bool fits =
+      pair_smem_layout(pp.n_pad, pp.nbp, pp.nslots, (int)pp.chunks.size()).total <= 226 * 1024;
+    info[0] = (pp.ok && pp.ngroups <= kPMaxGroups && pp.nb < kPMaxBuckets && pp.nbp <= kPMaxBuckets && fits) ? 1 : 0;
+    info[1] = pp.ngroups;
+    info[2] = pp.nslots;
+    info[3] = pp.nb;
+    info[4] = (int)pp.chunks.size();
+    info[5] = ext;
+    info[6] = most;
+    info[7] = kSub;
+    if (phase) {
+      *phase = pp.sub_phi;
+    }
+    for (std::size_t i = 0; slot_bin && i < cap && i < (std::size_t)pp.nslots; ++i) {
+      slot_bin[i] = pp.bin_of_slot[i];
+    }
+  }
+
   // Plans are kept with their device copy (slot tables, hinge and line coefficients):
   // a repeated call with the same photon bins and F table uploads nothing.
   struct CachedPlan {

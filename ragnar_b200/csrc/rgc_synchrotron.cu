@@ -767,6 +767,24 @@ extern "C" {
     return RGC_OK;
   }
 
+  int rgc_pair_plan_describe(const float* bins_e_syn, size_t nbins, const float* tab_x,
+                             const float* tab_y, size_t tab_n, int info[8], float* phase,
+                             int* slot_bin, size_t cap) {
+    if (!bins_e_syn || !tab_x || !tab_y || !info) {
+      return fail(RGC_ERR_INVALID, "rgc_pair_plan_describe: null argument");
+    }
+    TablePlan tp;
+    RGC_TRY(make_table_plan(tab_x, tab_y, tab_n, tp));
+    std::vector<int> idx;
+    for (std::size_t j = 0; j < nbins; ++j) {
+      if (bins_e_syn[j] > 0.0f && std::isfinite(bins_e_syn[j])) {
+        idx.push_back((int)j);
+      }
+    }
+    pair_plan_describe(tp, bins_e_syn, idx, info, phase, slot_bin, cap);
+    return RGC_OK;
+  }
+
   int rgc_sort_rank_mode(int* mode) {
     if (mode) {
       *mode = pair_rank_mode();
