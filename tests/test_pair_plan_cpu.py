@@ -78,3 +78,33 @@ def test_random_bins_and_rejections(cabi_cpu, ftable):
     assert cabi_cpu.pair_plan_describe(cabi_cpu.logspace(0.01, 1e5, 200), tx, ty2)["eligible"] == 0
     # more bins than one launch takes
     assert _describe(cabi_cpu, cabi_cpu.logspace(1e-3, 1e6, 2500), ftable)["eligible"] == 0
+
+
+def test_sub_bucket_decomposition_identity():
+    """the identity the pair kernel rests on (rgc_sync_pair.cu header), in numpy fp64: for a bucket's
+    particles (fc_i, w_i) and a bin with threshold t, sum_i w_i max(0, fc_i - t) equals the pair sum over
+    the ONE sub-bucket s = floor(8 fc + phi) that contains t plus S1_s - t S0_s of the sub-buckets above
+    it; and for the cell next to the table's zero tail, sum_i w_i max(0, t - fc_i) equals
+    S0_run - sum w sat(fc + (1 - t)) on that sub-bucket plus t S0_s - S1_s of the sub-buckets below"""
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        n = int(rng.integers(1, 5000))
+        fc = rng.random(n)
+        w = rng.random(n) * 10 ** rng.uniform(-3, 3)
+        phi = rng.random()
+        s = np.minimum(np.floor(8 * fc + phi).astype(int), 8)
+        S0 = np.bincount(s, weights=w, minlength=9)
+        S1 = np.bincount(s, weights=w * fc, minlength=9)
+        for t in rng.random(8):
+            s0 = min(int(np.floor(8 * t + phi)), 8)
+            own = s == s0
+            # L form: hinge active above the threshold
+            direct = np.sum(w * np.maximum(0.0, fc - t))
+            pair = np.sum(w[own] * np.clip(fc[own] - t, 0.0, 1.0))
+            lin = np.sum(S1[s0 + 1:] - t * S0[s0 + 1:])
+            assert abs(direct - (pair + lin)) <= 1e-12 * max(1.0, abs(direct))
+            # zero-tail form: S0 of the run minus the saturated sum, moments of the sub-buckets below
+            direct_r = np.sum(w * np.maximum(0.0, t - fc))
+            pair_r = np.sum(w[own]) - np.sum(w[own] * np.clip(fc[own] + (1.0 - t), 0.0, 1.0))
+            lin_r = np.sum(t * S0[:s0] - S1[:s0])
+            assert abs(direct_r - (pair_r + lin_r)) <= 1e-12 * max(1.0, abs(direct_r))
