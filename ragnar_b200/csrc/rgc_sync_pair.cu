@@ -802,17 +802,20 @@ namespace rgc {
   //
   // One CTA of 16 warps per SM, warp-specialised:
   //   * warps 8-15 are two SORT groups of four warps.  Group g takes every other piece of the
-  //     CTA into buffer g: 32 coalesced 8-byte loads per thread, counting sort by sub-bucket
-  //     s = floor(8 fc + phi) in (thread, entry) order (6-bit per-thread counters of the 9
-  //     sub-buckets packed into one 64-bit register, warp scans of the counters packed two to a
-  //     register, warp totals through shared memory; no atomics), every run padded to a
-  //     multiple of 64 entries with zero-weight entries.
+  //     CTA into one of four buffers: 16 coalesced 16-byte loads (32 entries) per thread,
+  //     counting sort by sub-bucket s = floor(8 fc + phi) in (thread, entry) order (6-bit
+  //     per-thread counters of the 9 sub-buckets packed into one 64-bit register, warp scans of
+  //     the counters packed two to a register, warp totals through shared memory, private
+  //     cursor columns for the scatter; no atomics), every run padded to a multiple of 64
+  //     entries with zero-weight entries.
   //   * warps 0-7 are the RUN warps: warp w streams run w of the piece (warp 0 also run 8: with
   //     the phase shift runs 0 and 8 are the two parts of one eighth) through the lane groups
   //     that hold the bins whose threshold lies in that sub-bucket (plus, rarely, a
   //     neighbouring sub-bucket's groups, `extmask`), and adds ds_q * sum (fp64) into the CTA's
   //     row of partial sums with RED.ADD.F64 (a slot is only ever touched by one warp of the
-  //     CTA: the order of additions is fixed).
+  //     CTA: the order of additions is fixed).  Pieces are dealt to the CTAs in consecutive
+  //     pairs; a pair of the same bucket is streamed as one (one lane-group set-up and one
+  //     transpose-reduction for both) — decided by the piece indices alone, never by timing.
   // The hand-over is a pair of named barriers per buffer (FULL: 128 sort threads arrive, 256
   // run threads wait; EMPTY: the other way round); with four buffers both sort groups work up to
   // two of their pieces ahead of the run warps.
